@@ -1,0 +1,131 @@
+"""Pin oracle/oracle.py against outputs of the reference itself (tests/golden,
+minted by oracle/make_golden.py) -- CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from news_recommendation_project_v2_b200 import synthetic as syn
+
+
+def _digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", ["latent_cfg1_d768_L512", "latent_default_d1024_L64"])
+def test_latent_pool_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    dim, L, B, S, seed = (int(g[k]) for k in ("dim", "L", "B", "S", "seed"))
+    sd = syn.make_latent_state_dict(dim, L, seed=seed)
+    assert _digest(sd) == str(g["sd_sha256"]), "weight generator drifted from the golden run"
+    assert sorted(sd.keys()) == list(g["keys"])
+    x, mask = syn.make_token_batch(B, S, dim, seed=seed + 1)
+    pooled = oracle.latent_pool(sd, x, mask, dtype=torch.float64).float().numpy()
+    # reference ran in fp32; oracle in fp64: tolerance = fp32 accumulation noise
+    np.testing.assert_allclose(pooled, g["pooled"], atol=2e-6, rtol=0)
+    un = oracle.latent_pool(sd, x[:1], None, dtype=torch.float64)[0].float().numpy()
+    np.testing.assert_allclose(un, g["unpooled0"], atol=2e-4, rtol=1e-5)
+    # fp32 oracle as well (the dtype the reference computes in)
+    pooled32 = oracle.latent_pool(sd, x, mask, dtype=torch.float32).numpy()
+    np.testing.assert_allclose(pooled32, g["pooled"], atol=2e-6, rtol=0)
+
+
+def test_latent_pool_mask_semantics():
+    sd = syn.make_latent_state_dict(64, 16, heads=2, dim_head=32, seed=5)
+    x, mask = syn.make_token_batch(3, 6, 64, seed=6, min_len=2)
+    base = oracle.latent_pool(sd, x, mask, heads=2, dim_head=32)
+    x2 = x.clone()
+    x2[mask == 0] = 123.0  # padded tokens never influence the output
+    assert torch.equal(base, oracle.latent_pool(sd, x2, mask, heads=2, dim_head=32))
+    m0 = mask.clone()
+    m0[1] = 0
+    out = oracle.latent_pool(sd, x, m0, heads=2, dim_head=32)
+    assert torch.isnan(out[1]).all() and not torch.isnan(out[0]).any()
+
+
+@pytest.mark.parametrize("name", ["final_small_d768", "final_large_d1024"])
+def test_final_attention_score_rank_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    dim, hidden, n_rows, n_imp, seed = (int(g[k]) for k in ("dim", "hidden", "n_rows", "n_imp", "seed"))
+    sd = syn.make_final_attention_state_dict(dim, hidden, seed=seed)
+    assert _digest(sd) == str(g["sd_sha256"])
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand=str(g["cand"]), seed=seed + 3)
+    out = oracle.final_second_attention_score(sd, table, imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len,
+                                              dtype=torch.float64)
+    np.testing.assert_allclose(out["user"].float().numpy(), g["user"], atol=3e-6, rtol=1e-5)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=2e-6, rtol=0)
+    ranks = np.concatenate(out["grouped_scores"])
+    ref_ranks = g["ranks"]
+    # fp64 oracle vs fp32 reference: ranks may differ only where adjacent scores are within noise
+    bad = np.flatnonzero(ranks != ref_ranks)
+    assert len(bad) <= 2, f"{len(bad)} rank mismatches"
+    # ranks from the reference's own score bits must be bit-exact
+    ranks_from_ref_scores = np.concatenate(oracle.rank_group_preds(g["scores"], imp.cand_len))
+    assert np.array_equal(ranks_from_ref_scores, ref_ranks)
+    # metrics from the reference's ranks
+    grouped = oracle.group_items(ref_ranks, imp.cand_len)
+    m = np.array([oracle.score_row(imp.labels[i], grouped[i]) for i in range(n_imp)])
+    np.testing.assert_allclose(m, g["metrics"], atol=1e-12, rtol=0)
+
+
+def test_separable_rows_equal_padded_forward():
+    """FinalAttention is separable per table row."""
+    sd = syn.make_final_attention_state_dict(32, 64, seed=3)
+    table = syn.make_table(50, 32, seed=4)
+    imp = syn.make_impressions(9, 50, h_max=7, seed=5)
+    u = oracle.user_vectors(sd, table, imp.hist_idx, imp.hist_len, batch=4)
+    X, Wl = oracle.final_attention_rows(sd, table)
+    E = torch.exp(Wl)
+    off = syn.csr_offsets(imp.hist_len)
+    for i in range(imp.n):
+        r = torch.from_numpy(imp.hist_idx[off[i]:off[i + 1]]).long()
+        ui = (X[r] * E[r]).sum(0) / (E[r].sum(0) + 1e-10)
+        torch.testing.assert_close(ui, u[i], atol=1e-12, rtol=1e-10)
+
+
+def test_small_cases(golden_dir):
+    g = _load(golden_dir, "small_cases")
+    t = torch.Generator().manual_seed(7)
+    table = torch.randn(11, 8, generator=t)
+    groups = [np.array([3, 1, 4], dtype=np.int32), np.array([10], dtype=np.int32),
+              np.array([0, 0, 5, 9, 2], dtype=np.int32), np.array([7, 8], dtype=np.int32)]
+    emb, msk = oracle.final_attention_eval_collate(groups, table)
+    assert np.array_equal(emb.numpy(), g["collate_emb"])
+    assert np.array_equal(msk.numpy(), g["collate_mask"]) and msk.dtype == torch.int32
+    ranks = np.concatenate(oracle.rank_group_preds(g["rank_scores"], g["rank_counts"]))
+    assert np.array_equal(ranks, g["rank_out"], equal_nan=True)
+    impressions = ["N1-0 N2-1 N3-0", "N2-0 N4-1", "N5-1 N1-0 N6-0 N7-0"]
+    history = ["N9 N1 N8", "N8", "N4 N9 N10 N2"]
+    sp = oracle.split_impressions_and_history(impressions, history)
+    assert list(sp["news_list"]) == list(g["split_news"])
+    for a, b in (("impression_rev_ind_array", "split_imp"), ("impression_len_list", "split_imp_len"),
+                 ("history_rev_ind_array", "split_hist"), ("history_len_list", "split_hist_len")):
+        assert np.array_equal(sp[a], g[b]) and sp[a].dtype == np.int32
+    lab = np.array([list(l) + [-1] * (4 - len(l)) for l in sp["labels"]])
+    assert np.array_equal(lab, g["split_labels"])
+
+
+def test_oracle_against_live_reference_if_present():
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    ref = ref_harness.load_reference(batch_size=16)
+    model = ref_harness.make_reference_latent_model(ref, 256, 32, seed=11)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    x, mask = syn.make_token_batch(3, 9, 256, seed=12, min_len=1)
+    with torch.no_grad():
+        want = model(x, mask)
+    got = oracle.latent_pool(sd, x, mask, dtype=torch.float32)
+    torch.testing.assert_close(got, want, atol=2e-6, rtol=0)
