@@ -1,0 +1,176 @@
+/*
+ * nrb200.h -- C ABI of the B200-native embedding-and-scoring hot path.
+ *
+ * Drop-in boundary for AhmedFahim-git/news_recommendation_project_v2.  The
+ * reference is pure Python on stock torch ops and has no FFI of its own
+ * (SURVEY.md section 8b); each entry point below names the reference call
+ * site(s) (file:line under src/news_rec_utils/) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - matrices are row-major, `ld*` / `*_stride` are in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call is asynchronous on `stream` and returns 0 on success or a
+ *     negative NRB_E_* code; nrb_last_error() gives the message (thread local);
+ *   - no call allocates device memory: callers pass a workspace sized by the
+ *     matching *_workspace_bytes() query;
+ *   - out-of-range row ids never fault: the kernels substitute row 0 and set
+ *     bit 0 of `*err_flag` (device int32), which the host turns into an
+ *     IndexError like torch indexing does.
+ *   - there is NO CPU implementation behind this ABI.
+ */
+#ifndef NRB200_H_
+#define NRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRB_OK 0
+#define NRB_E_INVALID (-1)   /* bad argument / unsupported shape            */
+#define NRB_E_CUDA (-2)      /* CUDA runtime / driver error                 */
+#define NRB_E_ARCH (-3)      /* device is not sm_100                        */
+#define NRB_E_WORKSPACE (-4) /* workspace too small                         */
+
+#define NRB_F32 0
+#define NRB_BF16 1
+
+/* user-encoder pooling applied to the gathered history rows */
+#define NRB_POOL_FINAL_ATTENTION 0 /* u = sum(x*e) / (sum(e) + 1e-10); modeling_utils.py:224-228 */
+#define NRB_POOL_MEAN_L2 1         /* u = normalize(mean(x));          latent_attention.py:165-170 */
+
+/* epilogues of the dense row kernels (nrb_linear) */
+#define NRB_EPI_NONE 0      /* y = acc (+ bias)                       */
+#define NRB_EPI_RELU 1      /* y = relu(acc + bias)                   modeling_utils.py:218-221 */
+#define NRB_EPI_EXP 2       /* y = exp(acc + bias)                    modeling_utils.py:224     */
+#define NRB_EPI_RESIDUAL 3  /* y = acc + bias + res                   latent_attention.py:162-163 */
+#define NRB_EPI_GEGLU 4     /* y[j] = a_j * gelu_erf(g_j), W rows interleaved (a0,g0,a1,g1..) latent_attention.py:24-27 */
+#define NRB_EPI_SOFTMAX 5   /* y = softmax over groups of `group` columns of acc*scale + bias; latent_attention.py:69-72 */
+
+typedef void* nrb_stream_t;
+
+const char* nrb_version(void);
+const char* nrb_last_error(void);
+/* 0 when `device` is a compute-capability 10.x GPU (B200). */
+int nrb_check_device(int device);
+int nrb_sm_count(int device);
+/* cumulative number of kernels this library has launched in the process (bench.py's gpu_launches). */
+long long nrb_kernel_launches(void);
+
+/* ---- Stage C: per-impression dense rank -------------------------------------------
+ * replaces data_utils.py:414-415 rank_group_preds = scipy.stats.rankdata(-x, "dense")
+ * per group.  ranks[j] = 1 + #{distinct scores in the group that are > scores[j]};
+ * a group containing a NaN gets rank 0 everywhere (host maps 0 -> NaN). */
+int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups,
+                   int32_t* ranks, nrb_stream_t stream);
+
+/* ---- Stage B: padded history gather -----------------------------------------------
+ * replaces data_utils.py:784-791 final_attention_eval_collate_fn (+ pad_to_maxlen
+ * :723-750): emb_out[g, s, :] = table[idx[offsets[g]+s], :] for s < len_g else 0;
+ * mask_out[g, s] = s < len_g.  emb_out has the table dtype. */
+int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, int dim, int64_t table_stride,
+                       const int32_t* idx, const int64_t* offsets, int64_t n_groups, int max_len,
+                       void* emb_out, int32_t* mask_out, int32_t* err_flag, nrb_stream_t stream);
+
+/* ---- Stage B+C fused: gather -> user vector -> cosine -> dense rank --------------------
+ * replaces data_model_helper.py:112-131 (get_final_attention_eval: CPU gather in
+ * DataLoader workers + user-encoder pooling), :200-230 (per-impression
+ * F.cosine_similarity loop, eps 1e-8, normalise-first) and data_utils.py:414-415.
+ *
+ *   hist_x / hist_e : per-row tables the pooling reads (hist_e NULL for MEAN_L2);
+ *                     for FINAL_ATTENTION they are the separable per-row outputs
+ *                     x and exp(logit) of nrb_final_attention_rows.
+ *   cand            : the table candidates are scored against (news_embeddings).
+ *   *_off           : int64 CSR offsets [n_imp + 1] into hist_idx / cand_idx.
+ *   user_out        : optional fp32 [n_imp, dim] (NULL to skip).
+ *   scores          : fp32 [cand_off[n_imp]] (absolute candidate positions).
+ *   ranks           : optional int32, same indexing.
+ * dim * elemsize must be a multiple of 512 bytes and at most 4096. */
+int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
+                   const void* hist_x, const void* hist_e, int64_t hist_stride,
+                   const void* cand, int64_t cand_stride,
+                   const int32_t* hist_idx, const int64_t* hist_off,
+                   const int32_t* cand_idx, const int64_t* cand_off, int64_t n_imp,
+                   float* user_out, float* scores, int32_t* ranks, int32_t* err_flag,
+                   nrb_stream_t stream);
+
+/* ---- dense row kernels -------------------------------------------------------------
+ * y[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]) -- the torch.nn.Linear contraction
+ * (latent_attention.py:65-74,33-37; modeling_utils.py:218-222).
+ *   precision NRB_BF16: a, w are bf16, tcgen05.mma (kind::f16) with fp32 TMEM accumulators,
+ *                       operands staged by TMA; K % 64 == 0, N % 16 == 0.
+ *   precision NRB_F32 : a, w are fp32, FFMA accumulation (the reference's own fp32 arithmetic).
+ * out_dtype selects the dtype of y (and of `res` for NRB_EPI_RESIDUAL, which is fp32).
+ * For GEGLU y has N/2 columns; for SOFTMAX `group` | N columns form one softmax row and
+ * `scale` multiplies acc before bias. */
+int nrb_linear(int precision, int epilogue, int out_dtype,
+               const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
+               const float* res, int64_t ldres, void* y, int64_t ldy,
+               int64_t M, int N, int K, int group, float scale, nrb_stream_t stream);
+
+/* ---- FinalAttention per-row transform -------------------------------------------------
+ * replaces the per-history-slot MLPs of modeling_utils.py:218-222 by one pass over the
+ * table (they depend only on the news row):
+ *   x = W3 relu(W2 relu(W1 e + b1) + b2) + b3 ; elog = exp(W5 relu(W4 x + b4)).
+ * Weights are in `precision` dtype, row-major [out,in] (torch Linear layout), biases fp32.
+ * x_out / e_out have `out_dtype`. */
+size_t nrb_final_attention_rows_workspace_bytes(int precision, int64_t n_rows, int dim, int hidden);
+int nrb_final_attention_rows(int precision, int out_dtype, const void* table, int64_t table_stride,
+                             int64_t n_rows, int dim, int hidden,
+                             const void* w1, const float* b1, const void* w2, const float* b2,
+                             const void* w3, const float* b3, const void* w4, const float* b4,
+                             const void* w5, void* x_out, void* e_out, int64_t out_stride,
+                             void* workspace, size_t workspace_bytes, nrb_stream_t stream);
+
+/* ---- Stage A: latent-attention pooling ---------------------------------------------------
+ * replaces latent_attention.py:134-171 LatentAttentionModel.forward.
+ *
+ * nrb_latent_fold (once per weight set): K,V = to_kv(LN_ctx(latents)) are input independent
+ * (latent_attention.py:161,67), so they are projected once and folded into the per-head
+ * matrices  A[h*Lp + l, :] = (Wq_h^T k_{h,l}) * dim_head^-0.5   ([heads*Lp, dim])
+ *           B[:, h*Lp + l] =  Wout_h v_{h,l}                    ([dim, heads*Lp])
+ * so that logits = LN(x) A^T and attn_out = softmax(logits) B^T.  Lp = L rounded up to a
+ * multiple of 16; padded latents get -inf logits.  All inputs fp32; A,B written in `precision`.
+ *
+ * nrb_latent_forward: x[B,S,dim] (fp32 or bf16) + lengths -> pooled[B,dim] fp32 (masked mean,
+ * L2-normalised), or un-pooled fp32 [B,S,dim] when pooled_out is NULL.  Padded tokens are never
+ * computed (they cannot influence the output).  `token_mask` is the reference's
+ * attention_mask int32 [B,S]; it may be any 0/1 pattern. */
+size_t nrb_latent_fold_workspace_bytes(int dim, int heads, int dim_head, int num_latents);
+int nrb_latent_fold(int precision, int dim, int heads, int dim_head, int num_latents,
+                    const float* latents, const float* ln_ctx_w, const float* ln_ctx_b,
+                    const float* w_q, const float* w_kv, const float* w_out,
+                    void* a_out, void* b_out, void* workspace, size_t workspace_bytes,
+                    nrb_stream_t stream);
+
+typedef struct nrb_latent_weights {
+  int precision;        /* NRB_BF16 | NRB_F32: dtype of a, b, w_ff1, w_ff2            */
+  int dim, heads, num_latents, latents_padded;
+  const void* a;        /* [heads*Lp, dim]   from nrb_latent_fold                     */
+  const void* b;        /* [dim, heads*Lp]                                            */
+  const float* ln1_w;   /* cross_attend_blocks.0.norm                                 */
+  const float* ln1_b;
+  const float* ln2_w;   /* cross_attend_blocks.1.norm                                 */
+  const float* ln2_b;
+  const void* w_ff1;    /* [8*dim, dim] rows interleaved (a0,g0,a1,g1,...)            */
+  const float* b_ff1;   /* [8*dim] interleaved the same way                           */
+  const void* w_ff2;    /* [dim, 4*dim]                                               */
+  const float* b_ff2;   /* [dim]                                                      */
+} nrb_latent_weights;
+
+size_t nrb_latent_forward_workspace_bytes(const nrb_latent_weights* w, int64_t max_tokens);
+int nrb_latent_forward(const nrb_latent_weights* w, const void* x, int x_dtype,
+                       int64_t batch, int seq, const int32_t* token_mask,
+                       float* pooled_out, float* unpooled_out,
+                       void* workspace, size_t workspace_bytes, int64_t max_tokens,
+                       int64_t* n_tokens_host, nrb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRB200_H_ */

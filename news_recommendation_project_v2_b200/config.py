@@ -1,0 +1,39 @@
+"""Module constants, mirroring the reference's `news_rec_utils/config.py:19-43`.
+
+The reference reads model dimensions from these globals at construction time
+(latent_attention.py:91-113); the drop-in modules accept keyword overrides and
+fall back to these values.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")  # config.py:19
+EMBEDDING_DIM = 1024  # config.py:29
+REDUCED_DIM = EMBEDDING_DIM  # config.py:31
+IMPRESSION_MAXLEN = 600  # config.py:33
+NUM_WORKERS = 4  # config.py:43
+TORCH_DTYPE = torch.float32  # config.py:39
+
+# Arithmetic of the CUDA hot path:
+#   "bf16": bf16 tables / weights, tcgen05 tensor cores with fp32 accumulation (throughput path)
+#   "fp32": fp32 tables / weights, FFMA accumulation (the reference's own arithmetic; parity path)
+PRECISION = os.environ.get("NRB200_PRECISION", "bf16")
+
+# Tokens processed per latent-attention chunk (bounds the workspace: ~42 KB / token in bf16 at d=768, L=512).
+LATENT_MAX_TOKENS = int(os.environ.get("NRB200_LATENT_MAX_TOKENS", "65536"))
+
+
+def precision_dtype(precision: str | torch.dtype | None = None) -> torch.dtype:
+    p = PRECISION if precision is None else precision
+    if isinstance(p, torch.dtype):
+        if p in (torch.float32, torch.bfloat16):
+            return p
+        raise ValueError(f"unsupported precision {p}")
+    if p in ("bf16", "bfloat16"):
+        return torch.bfloat16
+    if p in ("fp32", "float32"):
+        return torch.float32
+    raise ValueError(f"unsupported precision {p!r} (use 'bf16' or 'fp32')")

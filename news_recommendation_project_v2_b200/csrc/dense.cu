@@ -1,0 +1,253 @@
+// Row-wise helper kernels around the dense contractions + the FinalAttention per-row transform.
+//
+//   layer_norm_rows  : torch.nn.LayerNorm (eps 1e-5, biased variance) -- latent_attention.py:10-19
+//   softmax_groups   : softmax over the latents of one head           -- latent_attention.py:69-72
+//   nrb_final_attention_rows : modeling_utils.py:218-224 hoisted from per-history-slot to per-table-row
+#include "dense.cuh"
+
+#include <algorithm>
+
+namespace nrb {
+
+__device__ __forceinline__ float load_elem(const void* p, int dt, int64_t i) {
+  return dt == NRB_F32 ? reinterpret_cast<const float*>(p)[i]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_elem(void* p, int dt, int64_t i, float v) {
+  if (dt == NRB_F32)
+    reinterpret_cast<float*>(p)[i] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// One warp per row.  Two-pass mean / variance in fp32 like ATen's LayerNorm; the row is re-read
+// from L1 rather than cached so that any `dim` works.  Optionally gathers the source row through
+// `row_map` (varlen token packing) and emits an fp32 copy of the raw row (the residual operand).
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,
+                  const float* beta, void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy,
+                  int64_t rows, const int* rows_dev, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = rows_dev != nullptr ? min(rows, (int64_t)*rows_dev) : rows;
+  for (int64_t r = warp_id; r < n; r += n_warps) {
+    const int64_t src = row_map != nullptr ? (int64_t)row_map[r] : r;
+    const int64_t xo = src * ldx;
+    float s = 0.f;
+    for (int i = lane; i < dim; i += 32) s += load_elem(x, x_dtype, xo + i);
+    const float mean = warp_sum(s) / (float)dim;
+    float q = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+      const float d = load_elem(x, x_dtype, xo + i) - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)dim + 1e-5f);
+    for (int i = lane; i < dim; i += 32) {
+      const float v = load_elem(x, x_dtype, xo + i);
+      store_elem(y, y_dtype, r * ldy + i, (v - mean) * rstd * gamma[i] + beta[i]);
+      if (copy_f32 != nullptr) copy_f32[r * ldcopy + i] = v;
+    }
+  }
+}
+
+int layer_norm_rows(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,
+                    const float* beta, void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy,
+                    int64_t rows, const int* rows_dev, int dim, cudaStream_t st) {
+  if (rows <= 0) return NRB_OK;
+  const int64_t want = (rows + 7) / 8;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 16);
+  layer_norm_kernel<<<grid, 256, 0, st>>>(x, x_dtype, ldx, row_map, gamma, beta, y, y_dtype, ldy, copy_f32, ldcopy,
+                                          rows, rows_dev, dim); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+// One warp per (row, group): p = softmax(logits[group]) over the first `valid` columns of the group,
+// zeros in the padded columns.
+__global__ void __launch_bounds__(256)
+softmax_groups_kernel(const float* logits, int64_t ldl, void* p, int p_dtype, int64_t ldp, int64_t rows,
+                      const int* rows_dev, int n_groups, int group, int valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = rows_dev != nullptr ? min(rows, (int64_t)*rows_dev) : rows;
+  const int64_t total = n * n_groups;
+  for (int64_t w = warp_id; w < total; w += n_warps) {
+    const int64_t r = w / n_groups;
+    const int g = (int)(w - r * n_groups);
+    const float* src = logits + r * ldl + (int64_t)g * group;
+    float m = -INFINITY;
+    for (int i = lane; i < valid; i += 32) m = fmaxf(m, src[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < valid; i += 32) s += expf(src[i] - m);
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int i = lane; i < group; i += 32) {
+      const float v = i < valid ? expf(src[i] - m) * inv : 0.f;
+      store_elem(p, p_dtype, r * ldp + (int64_t)g * group + i, v);
+    }
+  }
+}
+
+int softmax_groups(const float* logits, int64_t ldl, void* p, int p_dtype, int64_t ldp, int64_t rows,
+                   const int* rows_dev, int n_groups, int group, int valid, cudaStream_t st) {
+  if (rows <= 0) return NRB_OK;
+  const int64_t want = (rows * n_groups + 7) / 8;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 16);
+  softmax_groups_kernel<<<grid, 256, 0, st>>>(logits, ldl, p, p_dtype, ldp, rows, rows_dev, n_groups, group, valid); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+                    int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    store_elem(dst, dst_dtype, r * ldd + c, load_elem(src, src_dtype, r * lds + c));
+  }
+}
+
+int convert_rows(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows,
+                 int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return NRB_OK;
+  const int64_t want = (rows * cols + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
+  convert_rows_kernel<<<grid, 256, 0, st>>>(src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+__global__ void transpose_f32_kernel(const float* src, int rows, int cols, float* dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(int64_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+int transpose_f32(const float* src, int rows, int cols, float* dst, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_f32_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+__global__ void scale_cols_kernel(float* x, int64_t ld, int64_t rows, int cols, float s) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    x[r * ld + (i - r * cols)] *= s;
+  }
+}
+
+int scale_cols_f32(float* x, int64_t ld, int64_t rows, int cols, float s, cudaStream_t st) {
+  const int64_t want = (rows * cols + 255) / 256;
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sm_count_cached() * 8);
+  scale_cols_kernel<<<grid, 256, 0, st>>>(x, ld, rows, cols, s); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+int linear(int precision, int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
+           const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
+           int N, int K, cudaStream_t st) {
+  if (precision == NRB_BF16)
+    return gemm_bf16_tc(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st);
+  if (precision == NRB_F32)
+    return gemm_f32_simt(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st);
+  set_error("nrb_linear: bad precision %d", precision);
+  return NRB_E_INVALID;
+}
+
+constexpr int64_t kFaChunkRows = 16384;
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_linear(int precision, int epilogue, int out_dtype, const void* a, int64_t lda, const void* w,
+                          int64_t ldw, const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy,
+                          int64_t M, int N, int K, int group, float scale, nrb_stream_t stream) {
+  (void)group;
+  (void)scale;
+  NRB_REQUIRE(a && w && y, "nrb_linear: null pointer");
+  NRB_REQUIRE(epilogue != NRB_EPI_SOFTMAX, "nrb_linear: the softmax epilogue is only reachable through nrb_latent_forward");
+  return linear(precision, epilogue, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, nullptr, N, K,
+                as_stream(stream));
+}
+
+extern "C" size_t nrb_final_attention_rows_workspace_bytes(int precision, int64_t n_rows, int dim, int hidden) {
+  const int64_t chunk = std::min<int64_t>(n_rows, kFaChunkRows);
+  Workspace ws(nullptr, 0);
+  ws.take((size_t)chunk * hidden * dtype_size(precision));  // h1
+  ws.take((size_t)chunk * hidden * dtype_size(precision));  // h2
+  ws.take((size_t)chunk * dim * dtype_size(precision));     // x in compute dtype
+  return ws.used + 256;
+}
+
+extern "C" int nrb_final_attention_rows(int precision, int out_dtype, const void* table, int64_t table_stride,
+                                        int64_t n_rows, int dim, int hidden, const void* w1, const float* b1,
+                                        const void* w2, const float* b2, const void* w3, const float* b3,
+                                        const void* w4, const float* b4, const void* w5, void* x_out, void* e_out,
+                                        int64_t out_stride, void* workspace, size_t workspace_bytes,
+                                        nrb_stream_t stream) {
+  NRB_REQUIRE(precision == NRB_F32 || precision == NRB_BF16, "nrb_final_attention_rows: bad precision");
+  NRB_REQUIRE(out_dtype == NRB_F32 || out_dtype == NRB_BF16, "nrb_final_attention_rows: bad out_dtype");
+  NRB_REQUIRE(n_rows > 0 && dim > 0 && hidden > 0, "nrb_final_attention_rows: bad sizes");
+  NRB_REQUIRE(table && w1 && b1 && w2 && b2 && w3 && b3 && w4 && b4 && w5 && x_out && e_out && workspace,
+              "nrb_final_attention_rows: null pointer");
+  if (workspace_bytes < nrb_final_attention_rows_workspace_bytes(precision, n_rows, dim, hidden)) {
+    set_error("nrb_final_attention_rows: workspace too small");
+    return NRB_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const size_t es = dtype_size(precision), os = dtype_size(out_dtype);
+  const int64_t chunk = std::min<int64_t>(n_rows, kFaChunkRows);
+  Workspace ws(workspace, workspace_bytes);
+  void* h1 = ws.take((size_t)chunk * hidden * es);
+  void* h2 = ws.take((size_t)chunk * hidden * es);
+  void* xc = ws.take((size_t)chunk * dim * es);
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n_rows - r0);
+    const void* e = (const char*)table + (size_t)r0 * table_stride * es;
+    void* xo = (char*)x_out + (size_t)r0 * out_stride * os;
+    void* eo = (char*)e_out + (size_t)r0 * out_stride * os;
+    int rc;
+    // x = W3 relu(W2 relu(W1 e + b1) + b2) + b3          (modeling_utils.py:218-220)
+    if ((rc = linear(precision, NRB_EPI_RELU, precision, e, table_stride, w1, dim, b1, nullptr, 0, h1, hidden, m,
+                     nullptr, hidden, dim, st)) != NRB_OK)
+      return rc;
+    if ((rc = linear(precision, NRB_EPI_RELU, precision, h1, hidden, w2, hidden, b2, nullptr, 0, h2, hidden, m,
+                     nullptr, hidden, hidden, st)) != NRB_OK)
+      return rc;
+    if ((rc = linear(precision, NRB_EPI_NONE, out_dtype, h2, hidden, w3, hidden, b3, nullptr, 0, xo, out_stride, m,
+                     nullptr, dim, hidden, st)) != NRB_OK)
+      return rc;
+    const void* xin = xo;
+    int64_t ldxin = out_stride;
+    if (out_dtype != precision) {
+      if ((rc = convert_rows(xo, out_dtype, out_stride, xc, precision, dim, m, dim, st)) != NRB_OK) return rc;
+      xin = xc;
+      ldxin = dim;
+    }
+    // elog = exp(W5 relu(W4 x + b4))                        (modeling_utils.py:221-224)
+    if ((rc = linear(precision, NRB_EPI_RELU, precision, xin, ldxin, w4, dim, b4, nullptr, 0, h1, hidden, m,
+                     nullptr, hidden, dim, st)) != NRB_OK)
+      return rc;
+    if ((rc = linear(precision, NRB_EPI_EXP, out_dtype, h1, hidden, w5, hidden, nullptr, nullptr, 0, eo,
+                     out_stride, m, nullptr, dim, hidden, st)) != NRB_OK)
+      return rc;
+  }
+  return NRB_OK;
+}

@@ -1,0 +1,443 @@
+// Stage B + C: clicked-history gather -> user vector -> cosine scores -> dense rank.
+//
+// Replaces (reference, src/news_rec_utils/):
+//   data_utils.py:784-791      final_attention_eval_collate_fn (CPU gather in DataLoader workers)
+//   modeling_utils.py:224-228  FinalAttention pooling (exp-weights, masked normalise, weighted sum)
+//   latent_attention.py:165-170 masked mean + F.normalize (LatentAttention as user encoder)
+//   data_model_helper.py:200-230 per-impression F.cosine_similarity loop
+//   data_utils.py:414-415      scipy.stats.rankdata(-x, "dense") per impression
+//
+// Bandwidth-bound design: ONE WARP PER IMPRESSION.  A table row is read with coalesced
+// 128-bit loads (lane l owns 16-byte vectors l, l+32, ...), history rows are accumulated in
+// fp32 registers, the user vector never leaves the register file, each candidate row is
+// reduced with warp shuffles and the impression's scores are ranked in shared memory by the
+// same warp.  Algorithmic bytes per impression: (r*H + C)*d*e + 4(H+C) + 8C  (SURVEY 8d).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace nrb {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kRankCap = 512;  // scores of one impression staged in smem (per warp)
+
+// Dense rank (descending) of s[0..n) by one warp.  r is output AND scratch: bit 31 of r[k]
+// temporarily holds "k is the first occurrence of its value".  rank_j = 1 + number of
+// distinct values greater than s_j; equal scores (incl. -0.0 == 0.0) share a rank; any NaN
+// makes the whole group rank 0 (scipy nan_policy 'propagate' -> host maps 0 to NaN).
+__device__ __forceinline__ void warp_dense_rank(const float* s, int32_t* r, int n, int lane) {
+  bool has_nan = false;
+  for (int k = lane; k < n; k += 32) has_nan |= (s[k] != s[k]);
+  if (__any_sync(kFullMask, has_nan)) {
+    for (int k = lane; k < n; k += 32) r[k] = 0;
+    return;
+  }
+  for (int k = lane; k < n; k += 32) {
+    const float v = s[k];
+    int first = 1;
+    for (int m = 0; m < k; ++m) first &= (s[m] != v);
+    r[k] = first ? (int32_t)0x80000000 : 0;
+  }
+  __syncwarp();
+  for (int j = lane; j < n; j += 32) {
+    const float v = s[j];
+    int cnt = 1;
+    for (int k = 0; k < n; ++k) cnt += (int)(s[k] > v) & (int)((uint32_t)r[k] >> 31);
+    r[j] = (r[j] & (int32_t)0x80000000) | cnt;
+  }
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) r[k] &= 0x7fffffff;
+}
+
+struct ScoreRankParams {
+  const char* hist_x;
+  const char* hist_e;
+  const char* cand;
+  int64_t hist_stride_bytes;
+  int64_t cand_stride_bytes;
+  const int32_t* hist_idx;
+  const int64_t* hist_off;
+  const int32_t* cand_idx;
+  const int64_t* cand_off;
+  int64_t n_imp;
+  int64_t n_rows;
+  int dim;
+  float* user_out;
+  float* scores;
+  int32_t* ranks;
+  int32_t* err_flag;
+};
+
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const char* base, int lane, uint4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = ldg_stream_128(base + (size_t)(lane + 32 * i) * 16);
+}
+
+template <typename T, int NV, int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+score_rank_kernel(const ScoreRankParams p) {
+  constexpr int EPV = Vec16<T>::EPV;
+  constexpr int EPL = NV * EPV;  // elements owned by one lane
+  __shared__ float s_scores[kWarpsPerCta][kRankCap];
+  __shared__ int32_t s_ranks[kWarpsPerCta][kRankCap];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+
+  for (int64_t imp = (int64_t)blockIdx.x * kWarpsPerCta + warp; imp < p.n_imp; imp += stride) {
+    const int64_t h0 = p.hist_off[imp], h1 = p.hist_off[imp + 1];
+    const int64_t c0 = p.cand_off[imp], c1 = p.cand_off[imp + 1];
+
+    float num[EPL];
+    float den[MODE == NRB_POOL_FINAL_ATTENTION ? EPL : 1];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) num[i] = 0.f;
+    if (MODE == NRB_POOL_FINAL_ATTENTION) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) den[i] = 0.f;
+    }
+
+    // ---- history: gather rows, accumulate in registers -------------------------------
+    for (int64_t base = h0; base < h1; base += 32) {
+      const int cnt = (int)min((int64_t)32, h1 - base);
+      int my = 0;
+      if (lane < cnt) {
+        my = p.hist_idx[base + lane];
+        if ((uint32_t)my >= (uint64_t)p.n_rows) {
+          atomicOr(p.err_flag, 1);
+          my = 0;
+        }
+      }
+      for (int s = 0; s < cnt; s += 2) {
+        const bool two = (s + 1 < cnt);  // warp-uniform
+        const int r0 = __shfl_sync(kFullMask, my, s);
+        const int r1 = __shfl_sync(kFullMask, my, two ? s + 1 : s);
+        uint4 x0[NV], x1[NV];
+        load_row<T, NV>(p.hist_x + (int64_t)r0 * p.hist_stride_bytes, lane, x0);
+        load_row<T, NV>(p.hist_x + (int64_t)r1 * p.hist_stride_bytes, lane, x1);
+        if (MODE == NRB_POOL_FINAL_ATTENTION) {
+          uint4 e0[NV], e1[NV];
+          load_row<T, NV>(p.hist_e + (int64_t)r0 * p.hist_stride_bytes, lane, e0);
+          load_row<T, NV>(p.hist_e + (int64_t)r1 * p.hist_stride_bytes, lane, e1);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            float xf[EPV], ef[EPV];
+            Vec16<T>::unpack(x0[i], xf);
+            Vec16<T>::unpack(e0[i], ef);
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) {
+              num[i * EPV + k] = fmaf(xf[k], ef[k], num[i * EPV + k]);
+              den[i * EPV + k] += ef[k];
+            }
+          }
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              float xf[EPV], ef[EPV];
+              Vec16<T>::unpack(x1[i], xf);
+              Vec16<T>::unpack(e1[i], ef);
+#pragma unroll
+              for (int k = 0; k < EPV; ++k) {
+                num[i * EPV + k] = fmaf(xf[k], ef[k], num[i * EPV + k]);
+                den[i * EPV + k] += ef[k];
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            float xf[EPV];
+            Vec16<T>::unpack(x0[i], xf);
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) num[i * EPV + k] += xf[k];
+          }
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              float xf[EPV];
+              Vec16<T>::unpack(x1[i], xf);
+#pragma unroll
+              for (int k = 0; k < EPV; ++k) num[i * EPV + k] += xf[k];
+            }
+          }
+        }
+      }
+    }
+
+    // ---- user vector ---------------------------------------------------------------------
+    float ss = 0.f;
+    if (MODE == NRB_POOL_FINAL_ATTENTION) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        num[i] = num[i] / (den[i] + 1e-10f);  // modeling_utils.py:225
+        ss = fmaf(num[i], num[i], ss);
+      }
+    } else {
+      const float cntf = (float)(h1 - h0);  // 0/0 -> NaN like the reference (latent_attention.py:168)
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        num[i] = num[i] / cntf;
+        ss = fmaf(num[i], num[i], ss);
+      }
+      const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);  // F.normalize eps
+      ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        num[i] = num[i] / nrm;
+        ss = fmaf(num[i], num[i], ss);
+      }
+    }
+    if (p.user_out != nullptr) {
+      float* dst = p.user_out + imp * (int64_t)p.dim;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int q = 0; q < EPV / 4; ++q) {
+          float4 o = make_float4(num[i * EPV + 4 * q], num[i * EPV + 4 * q + 1], num[i * EPV + 4 * q + 2],
+                                 num[i * EPV + 4 * q + 3]);
+          *reinterpret_cast<float4*>(dst + (size_t)(lane + 32 * i) * EPV + 4 * q) = o;
+        }
+      }
+    }
+    // F.cosine_similarity: x / max(|x|, 1e-8) first (data_model_helper.py:224-227)
+    const float unorm = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) num[i] = num[i] / unorm;
+
+    // ---- candidates: dot + norm per row, warp-shuffle reduction -------------------------
+    const int n_cand = (int)(c1 - c0);
+    for (int64_t base = c0; base < c1; base += 32) {
+      const int cnt = (int)min((int64_t)32, c1 - base);
+      int my = 0;
+      if (lane < cnt) {
+        my = p.cand_idx[base + lane];
+        if ((uint32_t)my >= (uint64_t)p.n_rows) {
+          atomicOr(p.err_flag, 1);
+          my = 0;
+        }
+      }
+      float my_score = 0.f;
+      for (int s = 0; s < cnt; s += 2) {
+        const bool two = (s + 1 < cnt);
+        const int r0 = __shfl_sync(kFullMask, my, s);
+        const int r1 = __shfl_sync(kFullMask, my, two ? s + 1 : s);
+        uint4 a0[NV], a1[NV];
+        load_row<T, NV>(p.cand + (int64_t)r0 * p.cand_stride_bytes, lane, a0);
+        load_row<T, NV>(p.cand + (int64_t)r1 * p.cand_stride_bytes, lane, a1);
+        float d0 = 0.f, q0 = 0.f, d1 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float f0[EPV], f1[EPV];
+          Vec16<T>::unpack(a0[i], f0);
+          Vec16<T>::unpack(a1[i], f1);
+#pragma unroll
+          for (int k = 0; k < EPV; ++k) {
+            d0 = fmaf(f0[k], num[i * EPV + k], d0);
+            q0 = fmaf(f0[k], f0[k], q0);
+            d1 = fmaf(f1[k], num[i * EPV + k], d1);
+            q1 = fmaf(f1[k], f1[k], q1);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          d0 += __shfl_xor_sync(kFullMask, d0, o);
+          q0 += __shfl_xor_sync(kFullMask, q0, o);
+          d1 += __shfl_xor_sync(kFullMask, d1, o);
+          q1 += __shfl_xor_sync(kFullMask, q1, o);
+        }
+        const float sc0 = d0 / fmaxf(sqrtf(q0), 1e-8f);
+        const float sc1 = d1 / fmaxf(sqrtf(q1), 1e-8f);
+        if (lane == s) my_score = sc0;
+        if (two && lane == s + 1) my_score = sc1;
+      }
+      if (lane < cnt) {
+        p.scores[base + lane] = my_score;
+        const int pos = (int)(base - c0) + lane;
+        if (pos < kRankCap) s_scores[warp][pos] = my_score;
+      }
+    }
+
+    // ---- dense rank -----------------------------------------------------------------------
+    if (p.ranks != nullptr) {
+      __syncwarp();
+      if (n_cand <= kRankCap) {
+        warp_dense_rank(s_scores[warp], s_ranks[warp], n_cand, lane);
+        __syncwarp();
+        for (int k = lane; k < n_cand; k += 32) p.ranks[c0 + k] = s_ranks[warp][k];
+      } else {
+        __threadfence_block();
+        warp_dense_rank(p.scores + c0, p.ranks + c0, n_cand, lane);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int MODE>
+static int launch_score_rank_nv(int nv, const ScoreRankParams& p, int grid, cudaStream_t st) {
+  const dim3 block(kWarpsPerCta * 32);
+  switch (nv) {
+#define NRB_CASE(N)                                                  \
+  case N:                                                            \
+    score_rank_kernel<T, N, MODE><<<grid, block, 0, st>>>(p); note_launch();        \
+    break;
+    NRB_CASE(1)
+    NRB_CASE(2)
+    NRB_CASE(3)
+    NRB_CASE(4)
+    NRB_CASE(5)
+    NRB_CASE(6)
+    NRB_CASE(7)
+    NRB_CASE(8)
+#undef NRB_CASE
+    default:
+      set_error("nrb_score_rank: dim*elemsize must be a multiple of 512 bytes and <= 4096 (got %d vectors/lane)", nv);
+      return NRB_E_INVALID;
+  }
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+// ---- standalone dense rank (rank_group_preds drop-in) ---------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+dense_rank_kernel(const float* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks) {
+  __shared__ float s_scores[kWarpsPerCta][kRankCap];
+  __shared__ int32_t s_ranks[kWarpsPerCta][kRankCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += stride) {
+    const int64_t c0 = offsets[g], c1 = offsets[g + 1];
+    const int64_t n64 = c1 - c0;
+    if (n64 <= kRankCap) {
+      const int n = (int)n64;
+      for (int k = lane; k < n; k += 32) s_scores[warp][k] = scores[c0 + k];
+      __syncwarp();
+      warp_dense_rank(s_scores[warp], s_ranks[warp], n, lane);
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) ranks[c0 + k] = s_ranks[warp][k];
+    } else {
+      warp_dense_rank(scores + c0, ranks + c0, (int)n64, lane);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- padded gather (final_attention_eval_collate_fn drop-in) -----------------------------------
+// one warp per (group, slot): copies one table row (or zeros) with 128-bit accesses.
+__global__ void __launch_bounds__(256)
+gather_collate_kernel(const char* table, int64_t n_rows, int row_bytes, int64_t table_stride_bytes,
+                      const int32_t* idx, const int64_t* offsets, int64_t n_groups, int max_len,
+                      char* emb_out, int32_t* mask_out, int32_t* err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = n_groups * (int64_t)max_len;
+  const int nvec = row_bytes / 16;
+  for (int64_t slot = warp_id; slot < total; slot += n_warps) {
+    const int64_t g = slot / max_len;
+    const int s = (int)(slot - g * max_len);
+    const int64_t o0 = offsets[g];
+    const int len = (int)(offsets[g + 1] - o0);
+    const bool valid = s < len;
+    uint4* dst = reinterpret_cast<uint4*>(emb_out + slot * (int64_t)row_bytes);
+    if (valid) {
+      int r = idx[o0 + s];
+      if ((uint32_t)r >= (uint64_t)n_rows) {
+        if (lane == 0) atomicOr(err_flag, 1);
+        r = 0;
+      }
+      const char* src = table + (int64_t)r * table_stride_bytes;
+      for (int v = lane; v < nvec; v += 32) dst[v] = ldg_stream_128(src + (size_t)v * 16);
+    } else {
+      for (int v = lane; v < nvec; v += 32) dst[v] = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0) mask_out[slot] = valid ? 1 : 0;
+  }
+}
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,
+                              nrb_stream_t stream) {
+  NRB_REQUIRE(n_groups >= 0, "nrb_dense_rank: n_groups < 0");
+  if (n_groups == 0) return NRB_OK;
+  NRB_REQUIRE(scores && offsets && ranks, "nrb_dense_rank: null pointer");
+  const int64_t want = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
+  dense_rank_kernel<<<grid, kWarpsPerCta * 32, 0, as_stream(stream)>>>(scores, offsets, n_groups, ranks); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+extern "C" int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, int dim, int64_t table_stride,
+                                  const int32_t* idx, const int64_t* offsets, int64_t n_groups, int max_len,
+                                  void* emb_out, int32_t* mask_out, int32_t* err_flag, nrb_stream_t stream) {
+  NRB_REQUIRE(dtype == NRB_F32 || dtype == NRB_BF16, "nrb_gather_collate: bad dtype %d", dtype);
+  const int es = dtype == NRB_F32 ? 4 : 2;
+  NRB_REQUIRE(dim > 0 && (dim * es) % 16 == 0, "nrb_gather_collate: dim*elemsize must be a multiple of 16 bytes");
+  NRB_REQUIRE((table_stride * es) % 16 == 0, "nrb_gather_collate: table stride must keep rows 16-byte aligned");
+  NRB_REQUIRE(n_groups >= 0 && max_len >= 0, "nrb_gather_collate: negative size");
+  if (n_groups == 0 || max_len == 0) return NRB_OK;
+  NRB_REQUIRE(table && idx && offsets && emb_out && mask_out && err_flag, "nrb_gather_collate: null pointer");
+  const int64_t total = n_groups * (int64_t)max_len;
+  const int64_t want = (total + 7) / 8;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
+  gather_collate_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      (const char*)table, n_rows, dim * es, table_stride * es, idx, offsets, n_groups, max_len, (char*)emb_out,
+      mask_out, err_flag); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+extern "C" int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows, const void* hist_x,
+                              const void* hist_e, int64_t hist_stride, const void* cand, int64_t cand_stride,
+                              const int32_t* hist_idx, const int64_t* hist_off, const int32_t* cand_idx,
+                              const int64_t* cand_off, int64_t n_imp, float* user_out, float* scores,
+                              int32_t* ranks, int32_t* err_flag, nrb_stream_t stream) {
+  NRB_REQUIRE(dtype == NRB_F32 || dtype == NRB_BF16, "nrb_score_rank: bad dtype %d", dtype);
+  NRB_REQUIRE(pool_mode == NRB_POOL_FINAL_ATTENTION || pool_mode == NRB_POOL_MEAN_L2,
+              "nrb_score_rank: bad pool_mode %d", pool_mode);
+  const int es = dtype == NRB_F32 ? 4 : 2;
+  NRB_REQUIRE(dim > 0 && (dim * es) % 512 == 0 && dim * es <= 4096,
+              "nrb_score_rank: dim*elemsize must be a multiple of 512 bytes and <= 4096 (dim=%d)", dim);
+  NRB_REQUIRE((hist_stride * es) % 16 == 0 && (cand_stride * es) % 16 == 0,
+              "nrb_score_rank: row strides must keep rows 16-byte aligned");
+  NRB_REQUIRE(n_imp >= 0 && n_rows > 0, "nrb_score_rank: bad sizes");
+  if (n_imp == 0) return NRB_OK;
+  NRB_REQUIRE(hist_x && cand && hist_idx && hist_off && cand_idx && cand_off && scores && err_flag,
+              "nrb_score_rank: null pointer");
+  NRB_REQUIRE(pool_mode != NRB_POOL_FINAL_ATTENTION || hist_e, "nrb_score_rank: hist_e required");
+  ScoreRankParams p;
+  p.hist_x = (const char*)hist_x;
+  p.hist_e = (const char*)hist_e;
+  p.cand = (const char*)cand;
+  p.hist_stride_bytes = hist_stride * es;
+  p.cand_stride_bytes = cand_stride * es;
+  p.hist_idx = hist_idx;
+  p.hist_off = hist_off;
+  p.cand_idx = cand_idx;
+  p.cand_off = cand_off;
+  p.n_imp = n_imp;
+  p.n_rows = n_rows;
+  p.dim = dim;
+  p.user_out = user_out;
+  p.scores = scores;
+  p.ranks = ranks;
+  p.err_flag = err_flag;
+  const int nv = dim * es / 512;
+  const int64_t want = (n_imp + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 64);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == NRB_F32) {
+    return pool_mode == NRB_POOL_FINAL_ATTENTION
+               ? launch_score_rank_nv<float, NRB_POOL_FINAL_ATTENTION>(nv, p, grid, st)
+               : launch_score_rank_nv<float, NRB_POOL_MEAN_L2>(nv, p, grid, st);
+  }
+  return pool_mode == NRB_POOL_FINAL_ATTENTION
+             ? launch_score_rank_nv<__nv_bfloat16, NRB_POOL_FINAL_ATTENTION>(nv, p, grid, st)
+             : launch_score_rank_nv<__nv_bfloat16, NRB_POOL_MEAN_L2>(nv, p, grid, st);
+}

@@ -1,0 +1,165 @@
+"""Device-resident scoring engine: table(s) + user-encoder row transform + fused score/rank.
+
+This is the host-side owner of what the reference spreads over
+`get_final_attention_eval` (data_model_helper.py:112-131, CPU gather in DataLoader
+workers + per-batch H2D/D2H), the per-impression cosine loop (:200-230) and
+`rank_group_preds` (data_utils.py:414-415).  Layout in HBM:
+
+  cand table  T  [N, d]  row r = news_list[r]   (scored against; `news_embeddings`)
+  hist tables X,E [N, d] FinalAttention's separable per-row outputs x and exp(logit)
+                         (or a single transformed table for mean-pool encoders)
+  CSR indices     int32 row ids + int64 offsets (from `*_rev_ind_array[0]` / `*_len_list`)
+
+All arithmetic happens in libnrb200.so; torch only owns the buffers.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .config import LATENT_MAX_TOKENS, precision_dtype
+from .synthetic import csr_offsets
+
+_table_cache: "dict[tuple, tuple[weakref.ref, torch.Tensor]]" = {}
+
+
+def resident_table(table: torch.Tensor, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """Upload (once) and cache a host table on the device in `dtype`."""
+    if table.is_cuda and table.dtype == dtype and table.is_contiguous():
+        return table
+    key = (id(table), table.data_ptr(), tuple(table.shape), table.dtype, dtype, device.index, table._version)
+    hit = _table_cache.get(key)
+    if hit is not None and hit[0]() is table:
+        return hit[1]
+    dev_t = table.detach().to(device=device, dtype=dtype, non_blocking=False).contiguous()
+    if len(_table_cache) > 8:
+        _table_cache.clear()
+    try:
+        _table_cache[key] = (weakref.ref(table), dev_t)
+    except TypeError:
+        pass
+    return dev_t
+
+
+def _as_i32(a, device) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.int32).contiguous()
+    arr = np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+    return torch.from_numpy(arr).to(device)
+
+
+def _offsets(lengths, device) -> tuple[torch.Tensor, int]:
+    if isinstance(lengths, torch.Tensor):
+        lengths = lengths.detach().cpu().numpy()
+    off = csr_offsets(np.asarray(lengths))
+    return torch.from_numpy(off).to(device), int(off[-1])
+
+
+def _final_attention_weights(model, dtype: torch.dtype, device) -> dict:
+    sd = model.state_dict()
+    need = [f"linear{i}.weight" for i in range(1, 6)] + [f"linear{i}.bias" for i in range(1, 5)]
+    for k in need:
+        if k not in sd:
+            raise _lib.NrbError(f"user encoder lacks {k}: not a FinalAttention state_dict")
+    w = {}
+    for k in need:
+        t = sd[k].detach().to(device)
+        w[k] = t.to(dtype).contiguous() if k.endswith("weight") else t.float().contiguous()
+    return w
+
+
+class ScoringEngine:
+    """table + user encoder -> (scores, dense ranks) for CSR impressions, all on one GPU."""
+
+    def __init__(self, news_embeddings: torch.Tensor, model: torch.nn.Module,
+                 query_news_embeddings: Optional[torch.Tensor] = None, precision=None,
+                 device: Optional[torch.device] = None):
+        self.device = _lib.require_device(device)
+        self.dtype = precision_dtype(precision)
+        self.model = model
+        self.n_rows, self.dim = news_embeddings.shape
+        with torch.cuda.device(self.device):
+            self.cand = resident_table(news_embeddings, self.dtype, self.device)
+            src = news_embeddings if query_news_embeddings is None else query_news_embeddings
+            hist_src = self.cand if query_news_embeddings is None else resident_table(src, self.dtype, self.device)
+            self.prepare_user_encoder(hist_src)
+
+    # -- per-row user-encoder transform (dense, once per table) --------------------------------
+    def prepare_user_encoder(self, hist_src: torch.Tensor) -> None:
+        from .latent_attention import LatentAttentionModel
+
+        if isinstance(self.model, LatentAttentionModel):
+            # tokens are independent: run the block once per table row, then mean-pool
+            fw = self.model.folded(self.dtype, self.device)
+            rows = ops.latent_forward(fw, hist_src.view(self.n_rows, 1, self.dim), None,
+                                      max_tokens=LATENT_MAX_TOKENS)
+            self.hist_x = rows.view(self.n_rows, self.dim).to(self.dtype).contiguous()
+            self.hist_e = None
+            self.pool_mode = _lib.POOL_MEAN_L2
+        else:
+            w = _final_attention_weights(self.model, self.dtype, self.device)
+            self.hist_x, self.hist_e = ops.final_attention_rows(hist_src, w, self.dtype)
+            self.pool_mode = _lib.POOL_FINAL_ATTENTION
+
+    # -- fused gather + pool + cosine + rank ---------------------------------------------------------
+    def upload_impressions(self, hist_idx, hist_len, cand_idx, cand_len):
+        n_imp = len(hist_len)
+        assert n_imp == len(cand_len), "Number of rows should be consistent"  # data_model_helper.py:183
+        h_off, n_h = _offsets(hist_len, self.device)
+        c_off, n_c = _offsets(cand_len, self.device)
+        assert n_c == len(cand_idx), "Number of impressions should match length of impression list"  # :186
+        assert n_h == len(hist_idx), "history index length should match history_len_list"
+        return (_as_i32(hist_idx, self.device), h_off, _as_i32(cand_idx, self.device), c_off, n_c)
+
+    def score_device(self, hist_idx_d, hist_off_d, cand_idx_d, cand_off_d, n_cand: int, want_user=False,
+                     want_ranks=True, err_flag=None, out_scores=None, out_ranks=None):
+        with torch.cuda.device(self.device):
+            return ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hist_idx_d, hist_off_d,
+                                  cand_idx_d, cand_off_d, n_cand, want_user=want_user, want_ranks=want_ranks,
+                                  err_flag=err_flag, out_scores=out_scores, out_ranks=out_ranks)
+
+    def score(self, hist_idx, hist_len, cand_idx, cand_len, want_user=False, want_ranks=True):
+        """Host arrays in, device tensors out: (user|None, scores fp32, ranks int32|None)."""
+        with torch.cuda.device(self.device):
+            hi, ho, ci, co, n_c = self.upload_impressions(hist_idx, hist_len, cand_idx, cand_len)
+            return self.score_device(hi, ho, ci, co, n_c, want_user=want_user, want_ranks=want_ranks)
+
+    def user_vectors(self, hist_idx, hist_len) -> torch.Tensor:
+        """get_final_attention_eval: fp32 [I, d] user vectors (device)."""
+        with torch.cuda.device(self.device):
+            n_imp = len(hist_len)
+            h_off, n_h = _offsets(hist_len, self.device)
+            assert n_h == len(hist_idx)
+            zeros = torch.zeros(n_imp + 1, dtype=torch.int64, device=self.device)
+            empty = torch.zeros(1, dtype=torch.int32, device=self.device)
+            user, _, _ = ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand,
+                                        _as_i32(hist_idx, self.device), h_off, empty, zeros, 0, want_user=True,
+                                        want_ranks=False)
+            return user
+
+
+_engine_cache: dict = {}
+
+
+def _model_fingerprint(model: torch.nn.Module) -> tuple:
+    return tuple((k, v.data_ptr(), v._version) for k, v in model.state_dict(keep_vars=True).items())
+
+
+def cached_engine(news_embeddings: torch.Tensor, model: torch.nn.Module,
+                  query_news_embeddings: Optional[torch.Tensor] = None, precision=None) -> ScoringEngine:
+    """Engines are expensive (table upload + dense row transform): reuse them while the table and
+    the weights are unchanged (the trainers call the hot path every epoch with new weights)."""
+    q = query_news_embeddings
+    key = (id(news_embeddings), news_embeddings.data_ptr(), news_embeddings._version,
+           None if q is None else (id(q), q.data_ptr(), q._version), id(model), _model_fingerprint(model),
+           str(precision_dtype(precision)))
+    eng = _engine_cache.get(key)
+    if eng is None:
+        _engine_cache.clear()
+        eng = ScoringEngine(news_embeddings, model, q, precision=precision)
+        _engine_cache[key] = eng
+    return eng

@@ -1,0 +1,94 @@
+"""Drop-in user encoder + model factories (reference: news_rec_utils/modeling_utils.py).
+
+  FinalAttention              modeling_utils.py:175-228
+  get_final_attention_model   modeling_utils.py:274-279
+  get_latent_attention_model  modeling_utils.py:151-155
+  get_model_eval              modeling_utils.py:402-417
+
+Same constructor signature, parameter names and state_dict keys as the reference.
+`forward` runs on the CUDA kernels: the five Linear layers go through
+`nrb_final_attention_rows` (tcgen05 / FFMA), the exp-weighted masked pooling
+through `nrb_score_rank`'s FINAL_ATTENTION pooling.  Inference only.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib, config, ops
+from .latent_attention import LatentAttentionModel
+
+
+class FinalAttention(nn.Module):
+    def __init__(self, reduced_dim: int, hidden_dim: int, precision=None):
+        super().__init__()
+        self.linear1 = nn.Linear(reduced_dim, hidden_dim)
+        self.dropout1 = nn.Dropout(0.1)  # inactive in eval; kept for attribute parity
+        self.linear2 = nn.Linear(hidden_dim, hidden_dim)
+        self.dropout2 = nn.Dropout(0.1)
+        self.linear3 = nn.Linear(hidden_dim, reduced_dim)
+        self.linear4 = nn.Linear(reduced_dim, hidden_dim)
+        self.dropout3 = nn.Dropout(0.1)
+        self.linear5 = nn.Linear(hidden_dim, reduced_dim, bias=False)
+        self.precision = precision
+
+    @torch.no_grad()
+    def forward(self, embeddings: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        """embeddings [B,H,d] (already masked), attention_mask [B,H] -> [B,d] (fp32)."""
+        if self.training:
+            raise _lib.NrbError("FinalAttention (nrb200) is inference only: call model.eval() (dropout / autograd "
+                                "are out of scope)")
+        from .engine import _final_attention_weights
+
+        in_dev = embeddings.device
+        dev = _lib.require_device(in_dev if in_dev.type == "cuda" else None)
+        dtype = config.precision_dtype(self.precision)
+        B, H, d = embeddings.shape
+        with torch.cuda.device(dev):
+            rows = embeddings.detach().to(device=dev, dtype=dtype).reshape(B * H, d).contiguous()
+            w = _final_attention_weights(self, dtype, dev)
+            # the MLPs act on each history slot independently (modeling_utils.py:218-222)
+            x, e = ops.final_attention_rows(rows, w, dtype)
+            valid = (attention_mask.to(dev) != 0)
+            lens = valid.sum(dim=1, dtype=torch.int64)
+            off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+            off[1:] = torch.cumsum(lens, 0)
+            idx = torch.nonzero(valid.reshape(-1), as_tuple=False).reshape(-1).to(torch.int32).contiguous()
+            if idx.numel() == 0:
+                idx = torch.zeros(1, dtype=torch.int32, device=dev)
+            zeros = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+            none_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+            user, _, _ = ops.score_rank(_lib.POOL_FINAL_ATTENTION, x, e, x, idx, off, none_idx, zeros, 0,
+                                        want_user=True, want_ranks=False)
+        return user if in_dev.type == "cuda" else user.to(in_dev)
+
+
+def get_final_attention_model(model_path: Optional[Path] = None) -> FinalAttention:
+    model = FinalAttention(reduced_dim=config.REDUCED_DIM, hidden_dim=4096)
+    if model_path:
+        model.load_state_dict(torch.load(model_path, weights_only=True))
+    return model.to(config.DEVICE).eval()
+
+
+def get_latent_attention_model(model_path: Optional[Path] = None) -> LatentAttentionModel:
+    model = LatentAttentionModel()
+    if model_path:
+        model.load_state_dict(torch.load(model_path, weights_only=True))
+    return model.to(config.DEVICE).eval()
+
+
+def get_model_eval(dataloader, model: nn.Module) -> torch.Tensor:
+    """Run `model` over a loader, results concatenated on the host (modeling_utils.py:402-417)."""
+    outs = []
+    model.eval()
+    with torch.no_grad():
+        for item in dataloader:
+            if isinstance(item, (tuple, list)):
+                res = model(*[t.to(config.DEVICE) for t in item])
+            else:
+                res = model(item.to(config.DEVICE))
+            outs.append(res.detach().cpu())
+    return torch.cat(outs)

@@ -1,0 +1,251 @@
+"""Tensor-level wrappers over the C ABI (device tensors in, device tensors out).
+
+These are the only places that call into libnrb200.so.  Every wrapper validates
+device / dtype / contiguity, passes raw pointers + the current torch stream and
+raises on a non-zero status.  No wrapper has a PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, LatentWeights, check, dtype_code, load, ptr, require_device, stream_ptr
+
+
+def _dev(t: torch.Tensor, name: str, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.NrbError(f"{name} must be a CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.NrbError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.NrbError(f"{name} must be contiguous")
+    return t
+
+
+def new_err_flag(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def raise_on_index_error(flag: torch.Tensor, what: str) -> None:
+    """Host-side check of the device error flag (synchronises)."""
+    if int(flag.item()) & 1:
+        raise IndexError(f"{what}: row index out of range for the embedding table")
+
+
+def dense_rank(scores: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """int32 dense ranks (0 = NaN group).  rank_group_preds, data_utils.py:414-415."""
+    require_device(scores.device)
+    _dev(scores, "scores", torch.float32)
+    _dev(offsets, "offsets", torch.int64)
+    n_groups = offsets.numel() - 1
+    ranks = torch.empty(scores.numel(), dtype=torch.int32, device=scores.device)
+    check(load().nrb_dense_rank(ptr(scores), ptr(offsets), n_groups, ptr(ranks), stream_ptr()), "nrb_dense_rank")
+    return ranks
+
+
+def gather_collate(table: torch.Tensor, idx: torch.Tensor, offsets: torch.Tensor, max_len: int,
+                   err_flag: Optional[torch.Tensor] = None):
+    """final_attention_eval_collate_fn on device (data_utils.py:784-791)."""
+    dev = require_device(table.device)
+    _dev(table, "table")
+    _dev(idx, "idx", torch.int32)
+    _dev(offsets, "offsets", torch.int64)
+    n_groups = offsets.numel() - 1
+    n_rows, dim = table.shape
+    emb = torch.empty(n_groups, max_len, dim, dtype=table.dtype, device=dev)
+    mask = torch.empty(n_groups, max_len, dtype=torch.int32, device=dev)
+    flag = err_flag if err_flag is not None else new_err_flag(dev)
+    check(load().nrb_gather_collate(ptr(table), dtype_code(table.dtype), n_rows, dim, table.stride(0), ptr(idx),
+                                    ptr(offsets), n_groups, max_len, ptr(emb), ptr(mask), ptr(flag), stream_ptr()),
+          "nrb_gather_collate")
+    if err_flag is None:
+        raise_on_index_error(flag, "gather_collate")
+    return emb, mask
+
+
+def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tensor], cand: torch.Tensor,
+               hist_idx: torch.Tensor, hist_off: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
+               n_cand_total: int, want_user: bool = False, want_ranks: bool = True,
+               err_flag: Optional[torch.Tensor] = None, out_scores: Optional[torch.Tensor] = None,
+               out_ranks: Optional[torch.Tensor] = None):
+    """Fused gather -> user vector -> cosine -> dense rank (nrb_score_rank)."""
+    dev = require_device(hist_x.device)
+    _dev(hist_x, "hist_x")
+    _dev(cand, "cand", hist_x.dtype)
+    if hist_e is not None:
+        _dev(hist_e, "hist_e", hist_x.dtype)
+        if hist_e.stride(0) != hist_x.stride(0):
+            raise _lib.NrbError("hist_x and hist_e must share the row stride")
+    for t, n in ((hist_idx, "hist_idx"), (cand_idx, "cand_idx")):
+        _dev(t, n, torch.int32)
+    for t, n in ((hist_off, "hist_off"), (cand_off, "cand_off")):
+        _dev(t, n, torch.int64)
+    n_imp = hist_off.numel() - 1
+    if cand_off.numel() - 1 != n_imp:
+        raise AssertionError("Number of rows should be consistent")  # data_model_helper.py:183-185
+    n_rows, dim = cand.shape
+    user = torch.empty(n_imp, dim, dtype=torch.float32, device=dev) if want_user else None
+    scores = out_scores if out_scores is not None else torch.empty(max(n_cand_total, 1), dtype=torch.float32, device=dev)
+    ranks = None
+    if want_ranks:
+        ranks = out_ranks if out_ranks is not None else torch.empty(max(n_cand_total, 1), dtype=torch.int32, device=dev)
+    flag = err_flag if err_flag is not None else new_err_flag(dev)
+    check(load().nrb_score_rank(pool_mode, dtype_code(hist_x.dtype), dim, min(n_rows, hist_x.shape[0]),
+                                ptr(hist_x), ptr(hist_e), hist_x.stride(0), ptr(cand), cand.stride(0),
+                                ptr(hist_idx), ptr(hist_off), ptr(cand_idx), ptr(cand_off), n_imp,
+                                ptr(user), ptr(scores), ptr(ranks), ptr(flag), stream_ptr()), "nrb_score_rank")
+    if err_flag is None:
+        raise_on_index_error(flag, "score_rank")
+    if out_scores is None:
+        scores = scores[:n_cand_total]
+    if want_ranks and out_ranks is None:
+        ranks = ranks[:n_cand_total]
+    return user, scores, ranks
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_NONE,
+           res: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """y = epilogue(a @ w.T + bias).  bf16 operands -> tcgen05, fp32 operands -> FFMA."""
+    dev = require_device(a.device)
+    _dev(a, "a")
+    _dev(w, "w", a.dtype)
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.NrbError("a / w inner dimensions differ")
+    out_dtype = out_dtype or a.dtype
+    n_out = N // 2 if epilogue == _lib.EPI_GEGLU else N
+    y = torch.empty(M, n_out, dtype=out_dtype, device=dev)
+    if bias is not None:
+        _dev(bias, "bias", torch.float32)
+    if res is not None:
+        _dev(res, "res", torch.float32)
+    check(load().nrb_linear(dtype_code(a.dtype), epilogue, dtype_code(out_dtype), ptr(a), a.stride(0), ptr(w),
+                            w.stride(0), ptr(bias), ptr(res), res.stride(0) if res is not None else 0, ptr(y),
+                            y.stride(0), M, N, K, 0, 1.0, stream_ptr()), "nrb_linear")
+    return y
+
+
+def final_attention_rows(table: torch.Tensor, weights: dict, out_dtype: torch.dtype):
+    """Per-row FinalAttention transform: (x, exp(logit)) tables (nrb_final_attention_rows).
+
+    `weights`: linear{1..5}.weight in table.dtype, linear{1..4}.bias in fp32, on device."""
+    dev = require_device(table.device)
+    _dev(table, "table")
+    n_rows, dim = table.shape
+    hidden = weights["linear1.weight"].shape[0]
+    prec = dtype_code(table.dtype)
+    for i in range(1, 6):
+        _dev(weights[f"linear{i}.weight"], f"linear{i}.weight", table.dtype)
+    for i in range(1, 5):
+        _dev(weights[f"linear{i}.bias"], f"linear{i}.bias", torch.float32)
+    lib = load()
+    ws_bytes = lib.nrb_final_attention_rows_workspace_bytes(prec, n_rows, dim, hidden)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    x = torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
+    e = torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
+    check(lib.nrb_final_attention_rows(
+        prec, dtype_code(out_dtype), ptr(table), table.stride(0), n_rows, dim, hidden,
+        ptr(weights["linear1.weight"]), ptr(weights["linear1.bias"]),
+        ptr(weights["linear2.weight"]), ptr(weights["linear2.bias"]),
+        ptr(weights["linear3.weight"]), ptr(weights["linear3.bias"]),
+        ptr(weights["linear4.weight"]), ptr(weights["linear4.bias"]),
+        ptr(weights["linear5.weight"]), ptr(x), ptr(e), dim, ptr(ws), ws_bytes, stream_ptr()),
+        "nrb_final_attention_rows")
+    return x, e
+
+
+@dataclass
+class FoldedLatent:
+    """Device-resident, kernel-ready weights of one LatentAttentionModel."""
+
+    precision: int
+    dim: int
+    heads: int
+    dim_head: int
+    num_latents: int
+    latents_padded: int
+    tensors: dict  # keeps the device tensors alive
+    struct: LatentWeights
+
+
+def latent_fold(sd: dict, heads: int, dim_head: int, precision: torch.dtype, device) -> FoldedLatent:
+    """One-time weight preparation (nrb_latent_fold + GEGLU row interleave)."""
+    dev = require_device(device)
+    f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()
+    lat = f32("latents")
+    L, dim = lat.shape
+    Lp = (L + 31) // 32 * 32
+    p0, p1 = "cross_attend_blocks.0.", "cross_attend_blocks.1."
+    wq, wkv, wout = f32(p0 + "fn.to_q.weight"), f32(p0 + "fn.to_kv.weight"), f32(p0 + "fn.to_out.weight")
+    if wq.shape != (heads * dim_head, dim):
+        raise _lib.NrbError(f"to_q.weight has shape {tuple(wq.shape)}, expected {(heads * dim_head, dim)}")
+    lnc_w, lnc_b = f32(p0 + "norm_context.weight"), f32(p0 + "norm_context.bias")
+    prec = dtype_code(precision)
+    lib = load()
+    a = torch.empty(heads * Lp, dim, dtype=precision, device=dev)
+    b = torch.empty(dim, heads * Lp, dtype=precision, device=dev)
+    ws_bytes = lib.nrb_latent_fold_workspace_bytes(dim, heads, dim_head, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.nrb_latent_fold(prec, dim, heads, dim_head, L, ptr(lat), ptr(lnc_w), ptr(lnc_b), ptr(wq), ptr(wkv),
+                              ptr(wout), ptr(a), ptr(b), ptr(ws), ws_bytes, stream_ptr()), "nrb_latent_fold")
+    # GEGLU: interleave the value / gate halves of net.0 so one accumulator tile holds both
+    w1, b1 = f32(p1 + "fn.net.0.weight"), f32(p1 + "fn.net.0.bias")
+    half = w1.shape[0] // 2
+    w1i = torch.stack([w1[:half], w1[half:]], dim=1).reshape(2 * half, dim).to(precision).contiguous()
+    b1i = torch.stack([b1[:half], b1[half:]], dim=1).reshape(2 * half).contiguous()
+    t = {
+        "a": a, "b": b,
+        "ln1_w": f32(p0 + "norm.weight"), "ln1_b": f32(p0 + "norm.bias"),
+        "ln2_w": f32(p1 + "norm.weight"), "ln2_b": f32(p1 + "norm.bias"),
+        "w_ff1": w1i, "b_ff1": b1i,
+        "w_ff2": f32(p1 + "fn.net.2.weight").to(precision).contiguous(), "b_ff2": f32(p1 + "fn.net.2.bias"),
+    }
+    torch.cuda.current_stream().synchronize()  # `ws` and the fp32 staging copies die here
+    st = LatentWeights(prec, dim, heads, L, Lp, *(ptr(t[k]) for k in
+                                                 ("a", "b", "ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_ff1", "b_ff1",
+                                                  "w_ff2", "b_ff2")))
+    return FoldedLatent(prec, dim, heads, dim_head, L, Lp, t, st)
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (avoids cudaMalloc in the steady state)."""
+    key = (dev.index,)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws_cache.pop(key, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+def latent_forward(fw: FoldedLatent, x: torch.Tensor, mask: Optional[torch.Tensor], max_tokens: int = 65536):
+    """LatentAttentionModel.forward on device: pooled [B,d] fp32 (mask given) or un-pooled [B,S,d]."""
+    dev = require_device(x.device)
+    _dev(x, "embeddings")
+    B, S, d = x.shape
+    if d != fw.dim:
+        raise _lib.NrbError(f"embedding dim {d} != model dim {fw.dim}")
+    lib = load()
+    max_tokens = max(int(max_tokens), S)
+    ws_bytes = lib.nrb_latent_forward_workspace_bytes(C.byref(fw.struct), max_tokens)
+    ws = _workspace(dev, ws_bytes)
+    if mask is not None:
+        _dev(mask, "attention_mask", torch.int32)
+        out = torch.empty(B, d, dtype=torch.float32, device=dev)
+        pooled, unpooled = ptr(out), None
+    else:
+        out = torch.empty(B, S, d, dtype=torch.float32, device=dev)
+        pooled, unpooled = None, ptr(out)
+    ntok = C.c_int64(-1)
+    check(lib.nrb_latent_forward(C.byref(fw.struct), ptr(x), dtype_code(x.dtype), B, S, ptr(mask), pooled, unpooled,
+                                 ptr(ws), ws.numel(), max_tokens, C.byref(ntok), stream_ptr()), "nrb_latent_forward")
+    return out

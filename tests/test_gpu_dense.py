@@ -1,0 +1,91 @@
+"""GPU parity: dense row kernels (tcgen05 bf16 / FFMA fp32) and the FinalAttention row transform.
+
+The floating-point reference for a single contraction is plain torch in fp32/fp64 on the SAME
+(already rounded) operands; the row transform is checked against the CPU oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from news_recommendation_project_v2_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from news_recommendation_project_v2_b200 import ops as _ops
+    return _ops
+
+
+def _ref_linear(a, w, bias, epi, res):
+    y = a.double() @ w.double().T
+    if bias is not None:
+        y = y + bias.double()
+    if epi == 1:
+        y = torch.relu(y)
+    elif epi == 2:
+        y = torch.exp(y)
+    elif epi == 3:
+        y = y + res.double()
+    elif epi == 4:
+        a_, g_ = y[:, 0::2], y[:, 1::2]  # interleaved (a0,g0,a1,g1,...)
+        y = a_ * 0.5 * g_ * (1 + torch.erf(g_ / math.sqrt(2)))
+    return y
+
+
+SHAPES = [(128, 256, 64), (1, 256, 128), (300, 768, 1024), (1000, 4096, 768), (257, 128, 256), (129, 64, 64),
+          (4099, 1024, 4096), (640, 6144, 768)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
+def test_linear_bf16_tcgen05(ops, M, N, K, epi):
+    g = torch.Generator().manual_seed(M * 7 + N + K + epi)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g) if epi == 3 else None
+    want = _ref_linear(a, w, bias, epi, res)
+    for out_dtype in (torch.float32, torch.bfloat16):
+        y = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, None if res is None else res.cuda(), out_dtype)
+        assert y.dtype == out_dtype and y.shape == want.shape
+        tol = 2e-4 if out_dtype == torch.float32 else 1.2e-2  # fp32 accumulate / one bf16 rounding (2^-8 rel)
+        torch.testing.assert_close(y.cpu().double(), want, atol=tol, rtol=tol)
+    # no-bias path
+    y = ops.linear(a.cuda(), w.cuda(), None, 0 if epi != 4 else 4, None, torch.float32)
+    torch.testing.assert_close(y.cpu().double(), _ref_linear(a, w, None, 0 if epi != 4 else 4, None), atol=2e-4, rtol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (1, 8, 16), (300, 768, 1024), (257, 4096, 768), (131, 136, 48)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
+def test_linear_fp32_ffma(ops, M, N, K, epi):
+    g = torch.Generator().manual_seed(M + N * 3 + K + epi)
+    a = torch.randn(M, K, generator=g) * 0.5
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g) if epi == 3 else None
+    want = _ref_linear(a, w, bias, epi, res)
+    y = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, None if res is None else res.cuda(), torch.float32)
+    torch.testing.assert_close(y.cpu().double(), want, atol=2e-5, rtol=2e-5)  # fp32 FFMA accumulation
+    yb = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, None if res is None else res.cuda(), torch.bfloat16)
+    torch.testing.assert_close(yb.cpu().double(), want, atol=1.2e-2, rtol=1.2e-2)
+
+
+@pytest.mark.parametrize("precision,tol", [(torch.float32, 2e-5), (torch.bfloat16, 4e-2)])
+def test_final_attention_rows_vs_oracle(ops, precision, tol):
+    dim, hidden, n = 768, 4096, 700
+    sd = syn.make_final_attention_state_dict(dim, hidden, seed=21)
+    table = syn.make_table(n, dim, seed=22)
+    want_x, want_logit = oracle.final_attention_rows(sd, table, dtype=torch.float64)
+    w = {k: (v.to(precision) if k.endswith("weight") else v.float()).cuda().contiguous() for k, v in sd.items()}
+    x, e = ops.final_attention_rows(table.to(precision).cuda(), w, torch.float32)
+    # fp32: FFMA accumulation noise; bf16: three to five chained bf16 contractions (rel 2^-8 each)
+    torch.testing.assert_close(x.cpu().double(), want_x, atol=tol, rtol=tol)
+    torch.testing.assert_close(e.cpu().double(), torch.exp(want_logit), atol=tol, rtol=tol)
+    xb, eb = ops.final_attention_rows(table.to(precision).cuda(), w, torch.bfloat16)
+    torch.testing.assert_close(xb.float().cpu().double(), want_x, atol=max(tol, 1e-2), rtol=max(tol, 1e-2))
+    assert eb.dtype == torch.bfloat16
