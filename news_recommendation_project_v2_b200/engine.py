@@ -35,7 +35,11 @@ def resident_table(table: torch.Tensor, dtype: torch.dtype, device: torch.device
     hit = _table_cache.get(key)
     if hit is not None and hit[0]() is table:
         return hit[1]
-    dev_t = table.detach().to(device=device, dtype=dtype, non_blocking=False).contiguous()
+    # copy in the source dtype first (a pinned table then crosses PCIe by DMA) and convert on the GPU
+    dev_t = table.detach().to(device=device, non_blocking=True)
+    if dev_t.dtype != dtype:
+        dev_t = dev_t.to(dtype)
+    dev_t = dev_t.contiguous()
     if len(_table_cache) > 8:
         _table_cache.clear()
     try:
