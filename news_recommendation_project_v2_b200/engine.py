@@ -105,8 +105,12 @@ class ScoringEngine:
             self.hist_e = None
             self.pool_mode = _lib.POOL_MEAN_L2
         else:
-            w = _final_attention_weights(self.model, self.dtype, self.device)
-            self.hist_x, self.hist_e = ops.final_attention_rows(hist_src, w, self.dtype)
+            # kernel-ready weights stay resident until a parameter changes (trainers update them per epoch)
+            fp = _model_fingerprint(self.model)
+            if getattr(self, "_fa_weights_key", None) != fp:
+                self._fa_weights = _final_attention_weights(self.model, self.dtype, self.device)
+                self._fa_weights_key = fp
+            self.hist_x, self.hist_e = ops.final_attention_rows(hist_src, self._fa_weights, self.dtype)
             self.pool_mode = _lib.POOL_FINAL_ATTENTION
 
     # -- fused gather + pool + cosine + rank ---------------------------------------------------------
