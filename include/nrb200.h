@@ -50,7 +50,7 @@ extern "C" {
 #define NRB_EPI_EXP 2       /* y = exp(acc + bias)                    modeling_utils.py:224     */
 #define NRB_EPI_RESIDUAL 3  /* y = acc + bias + res                   latent_attention.py:162-163 */
 #define NRB_EPI_GEGLU 4     /* y[j] = a_j * gelu_erf(g_j), W rows interleaved (a0,g0,a1,g1..) latent_attention.py:24-27 */
-#define NRB_EPI_SOFTMAX 5   /* y = softmax over groups of `group` columns of acc*scale + bias; latent_attention.py:69-72 */
+#define NRB_EPI_SOFTMAX 5   /* y = softmax over each group of `group` columns (first `group_valid` valid); latent_attention.py:69-72 */
 
 typedef void* nrb_stream_t;
 
@@ -103,15 +103,17 @@ int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
  * y[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]) -- the torch.nn.Linear contraction
  * (latent_attention.py:65-74,33-37; modeling_utils.py:218-222).
  *   precision NRB_BF16: a, w are bf16, tcgen05.mma (kind::f16) with fp32 TMEM accumulators,
- *                       operands staged by TMA; K % 64 == 0, N % 16 == 0.
+ *                       operands staged by TMA; K % 64 == 0, N % 32 == 0.
  *   precision NRB_F32 : a, w are fp32, FFMA accumulation (the reference's own fp32 arithmetic).
  * out_dtype selects the dtype of y (and of `res` for NRB_EPI_RESIDUAL, which is fp32).
- * For GEGLU y has N/2 columns; for SOFTMAX `group` | N columns form one softmax row and
- * `scale` multiplies acc before bias. */
+ * For GEGLU y has N/2 columns.  SOFTMAX (bf16 precision, bf16 output only): every `group` consecutive
+ * columns (a power of two in [32, 2048], N % 256 == 0) form one softmax row of which the first
+ * `group_valid` are real; groups wider than one 256-column tile are computed by a thread-block cluster
+ * that exchanges the row statistics through distributed shared memory. */
 int nrb_linear(int precision, int epilogue, int out_dtype,
                const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
                const float* res, int64_t ldres, void* y, int64_t ldy,
-               int64_t M, int N, int K, int group, float scale, nrb_stream_t stream);
+               int64_t M, int N, int K, int group, int group_valid, nrb_stream_t stream);
 
 /* ---- FinalAttention per-row transform -------------------------------------------------
  * replaces the per-history-slot MLPs of modeling_utils.py:218-222 by one pass over the
@@ -135,7 +137,7 @@ int nrb_final_attention_rows(int precision, int out_dtype, const void* table, in
  * matrices  A[h*Lp + l, :] = (Wq_h^T k_{h,l}) * dim_head^-0.5   ([heads*Lp, dim])
  *           B[:, h*Lp + l] =  Wout_h v_{h,l}                    ([dim, heads*Lp])
  * so that logits = LN(x) A^T and attn_out = softmax(logits) B^T.  Lp = L rounded up to a
- * multiple of 16; padded latents get -inf logits.  All inputs fp32; A,B written in `precision`.
+ * power of two (>= 32); padded latents get zero probability.  All inputs fp32; A,B written in `precision`.
  *
  * nrb_latent_forward: x[B,S,dim] (fp32 or bf16) + lengths -> pooled[B,dim] fp32 (masked mean,
  * L2-normalised), or un-pooled fp32 [B,S,dim] when pooled_out is NULL.  Padded tokens are never

@@ -161,9 +161,14 @@ int scale_cols_f32(float* x, int64_t ld, int64_t rows, int cols, float s, cudaSt
 
 int linear(int precision, int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
            const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
-           int N, int K, cudaStream_t st) {
+           int N, int K, cudaStream_t st, int group, int group_valid) {
   if (precision == NRB_BF16)
-    return gemm_bf16_tc(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st);
+    return gemm_bf16_tc(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, group,
+                        group_valid, st);
+  if (precision == NRB_F32 && epi == NRB_EPI_SOFTMAX) {
+    set_error("nrb_linear(fp32): the fused softmax epilogue exists only on the tensor-core path");
+    return NRB_E_INVALID;
+  }
   if (precision == NRB_F32)
     return gemm_f32_simt(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st);
   set_error("nrb_linear: bad precision %d", precision);
@@ -178,13 +183,10 @@ using namespace nrb;
 
 extern "C" int nrb_linear(int precision, int epilogue, int out_dtype, const void* a, int64_t lda, const void* w,
                           int64_t ldw, const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy,
-                          int64_t M, int N, int K, int group, float scale, nrb_stream_t stream) {
-  (void)group;
-  (void)scale;
+                          int64_t M, int N, int K, int group, int group_valid, nrb_stream_t stream) {
   NRB_REQUIRE(a && w && y, "nrb_linear: null pointer");
-  NRB_REQUIRE(epilogue != NRB_EPI_SOFTMAX, "nrb_linear: the softmax epilogue is only reachable through nrb_latent_forward");
   return linear(precision, epilogue, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, nullptr, N, K,
-                as_stream(stream));
+                as_stream(stream), group, group_valid);
 }
 
 extern "C" size_t nrb_final_attention_rows_workspace_bytes(int precision, int64_t n_rows, int dim, int hidden) {

@@ -1,18 +1,29 @@
 // Dense row kernel on the 5th-gen tensor cores:  y = epilogue(a[M,K] @ w[N,K]^T + bias).
 //
 // This is the torch.nn.Linear contraction of the reference (latent_attention.py:65-74,33-37;
-// modeling_utils.py:218-222), bf16 operands, fp32 accumulation.
+// modeling_utils.py:218-222), bf16 operands, fp32 accumulation, with the op that FOLLOWS the Linear in
+// the reference fused into the epilogue: ReLU / exp (FinalAttention), residual add, GEGLU with erf-GELU
+// (FeedForward), and the per-head softmax over the latents (SDPA, latent_attention.py:69-72).
 //
-// B200 design (one CTA per SM, persistent over output tiles, warp specialised):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D tiles of A (128x64) and W (BNx64) into a
-//              kStages-deep ring of 128B-swizzled shared-memory buffers, mbarrier complete_tx.
-//   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//              (M=128, N=BN, K=16) reading the smem ring through UMMA descriptors; accumulators live
-//              in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the
-//              mainloop of tile i+1; tcgen05.commit releases smem stages / publishes accumulators.
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> fused
-//              bias / ReLU / exp / residual / GEGLU -> vectorised global stores.
+// B200 design (one CTA per SM, persistent over output tiles, warp specialised, 384 threads):
+//   warp 0    : TMA producer -- cp.async.bulk.tensor 2-D tiles of A (128x64) and W (BNx64) into a
+//               ring of 128B-swizzled shared-memory stages, mbarrier complete_tx.
+//   warp 1    : MMA issuer   -- one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//               on UMMA smem descriptors; fp32 accumulators live in TMEM, double buffered (2 x BN columns)
+//               so the epilogue of tile i overlaps the mainloop of tile i+1; tcgen05.commit frees smem
+//               stages and publishes accumulators.
+//   warp 2    : TMEM allocator.
+//   warps 4-11: epilogue     -- two warps per TMEM lane quadrant, 128 accumulator columns each:
+//               tcgen05.ld (32 lanes x 32 columns) -> registers -> fused math -> either
+//                 * bf16 outputs: 128B-swizzled staging tile in smem -> TMA store (coalesced, async), or
+//                 * fp32 outputs: 128-bit global stores.
+//   softmax   : a softmax row (one head, Lp latents) spans Lp/256 N-tiles.  Those tiles are computed at the
+//               same time by the CTAs of one thread-block CLUSTER; the per-row (max, sum) statistics are
+//               exchanged through distributed shared memory (st.shared::cluster + remote mbarrier arrive),
+//               so probabilities are normalised with the exact row statistics before their single bf16
+//               rounding and P never exists in fp32 in HBM.
 #include "common.cuh"
+#include "dense.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -23,34 +34,77 @@ namespace nrb {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kCtrlWarps = 4;  // TMA, MMA, TMEM-alloc, spare
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = (kCtrlWarps + kEpiWarps) * 32;
+constexpr int kGroupBytes = kBM * 128;  // one 128-row x 64-column bf16 staging group (swizzle-128B)
+constexpr int kMaxCluster = 8;
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN>
+template <int BN, int EPI, bool OUT_BF16>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr bool kStaged = OUT_BF16;
+  static constexpr bool kSoftmax = EPI == NRB_EPI_SOFTMAX;
+  static constexpr int kHalves = BN / 128;  // epilogue column halves (128 accumulator columns each)
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kStaged ? kHalves * kGroupBytes : 0;
+  static constexpr int kXchgBytes = kSoftmax ? 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [step][participant][row]
+  static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXchgBytes;
+  static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(!kSoftmax || OUT_BF16, "softmax epilogue writes bf16 probabilities");
 };
 
 struct GemmParams {
-  int64_t M;             // row capacity (TMA extent); effective rows = min(M, *m_dev) when m_dev != NULL
-  const int* m_dev;      // optional device-side row count (varlen token packing, no host sync)
+  int64_t M;         // row capacity (TMA extent); effective rows = min(M, *m_dev) when m_dev != NULL
+  const int* m_dev;  // optional device-side row count (varlen token packing, no host sync)
   int N, K;
   const float* bias;
   const float* res;
   int64_t ldres;
-  void* y;
+  void* y;  // direct-store epilogues only
   int64_t ldy;
+  int group;        // softmax: padded group width Lp (power of two >= 32)
+  int group_valid;  // softmax: valid columns per group (L <= Lp)
+  int cluster;      // softmax: CTAs per cluster = max(1, Lp / 256)
 };
 
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
 
-template <int EPI, bool OUT_BF16>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const GemmParams& p, int64_t row, int col0) {
-  float v[32];
+// erf-GELU (F.gelu default, latent_attention.py:27): g * Phi(g) with Phi from the Abramowitz-Stegun 7.1.26
+// erfc approximation (|abs err| <= 1.5e-7, far below the bf16 rounding of the output); the negative branch
+// uses erfc directly so that there is no cancellation.
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+  const float z = fabsf(g) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * ex2_approx(-z * z * kLog2e);  // 0.5 * erfc(|z|)
+  const float cdf = g >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return g * cdf;
+}
+
+// ---- shared epilogue math: 32 accumulator columns of one row -> post-activation fp32 values -------------
+template <int EPI>
+__device__ __forceinline__ void activate_chunk(const uint32_t (&acc)[32], const GemmParams& p, int64_t row,
+                                               int col0, bool row_ok, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   if (p.bias != nullptr) {
@@ -68,84 +122,84 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (EPI == NRB_EPI_EXP) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = expf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j] * kLog2e);
   } else if (EPI == NRB_EPI_RESIDUAL) {
-    const float* r = p.res + row * p.ldres + col0;
+    if (row_ok) {
+      const float* r = p.res + row * p.ldres + col0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(r + j);
-      v[j] += b.x;
-      v[j + 1] += b.y;
-      v[j + 2] += b.z;
-      v[j + 3] += b.w;
-    }
-  }
-  if (EPI == NRB_EPI_GEGLU) {
-    // W rows interleaved (a0,g0,a1,g1,...): 32 accumulator columns -> 16 outputs
-    float o[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-    const int oc = col0 >> 1;
-    if (OUT_BF16) {
-      __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + oc;
-#pragma unroll
-      for (int j = 0; j < 16; j += 8) {
-        uint4 u = make_uint4(pack_bf16x2(o[j], o[j + 1]), pack_bf16x2(o[j + 2], o[j + 3]),
-                             pack_bf16x2(o[j + 4], o[j + 5]), pack_bf16x2(o[j + 6], o[j + 7]));
-        *reinterpret_cast<uint4*>(y + j) = u;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(r + j);
+        v[j] += b.x;
+        v[j + 1] += b.y;
+        v[j + 2] += b.z;
+        v[j + 3] += b.w;
       }
-    } else {
-      float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + oc;
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
     }
-    return;
-  }
-  if (OUT_BF16) {
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
+  } else if (EPI == NRB_EPI_GEGLU) {
+    // W rows interleaved (a0,g0,a1,g1,...): 32 accumulator columns -> 16 outputs in v[0..15]
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 u = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                           pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-      *reinterpret_cast<uint4*>(y + j) = u;
-    }
-  } else {
-    float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_fast(v[2 * j + 1]);
   }
+}
+
+// 16-byte chunk j (0..7) of row r inside a 128-row x 128-byte swizzle-128B staging group
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int j) {
+  return base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// NOUT consecutive bf16 outputs of row r, starting at 16-byte chunk j0 of the staging group
+template <int NOUT>
+__device__ __forceinline__ void stage_values(uint32_t base, int r, int j0, const float* v) {
+#pragma unroll
+  for (int q = 0; q < NOUT / 8; ++q)
+    st_shared_v4(stage_addr(base, r, j0 + q), pack_bf16x2(v[8 * q], v[8 * q + 1]),
+                 pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
+                 pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
 }
 
 template <int BN, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+               const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI, OUT_BF16>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kHalves = Cfg::kHalves;
+  constexpr bool kGeglu = EPI == NRB_EPI_GEGLU;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                    // [kStages] TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;         // [kStages] MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * kStages;     // [2] MMA -> epilogue
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // [kHalves][16 KB], 1024-aligned
+  float* xbuf = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][2*kMaxCluster][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kXchgBytes);
+  uint64_t* full_bar = bars;                      // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;           // [kStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;       // [2] MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* xbar = bars + 2 * kStages + 4;        // [2] softmax statistics exchange (max, sum)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int CS = Cfg::kSoftmax ? p.cluster : 1;
+  const uint32_t cta_rank = CS > 1 ? ptx::cluster_ctarank() : 0;
+  const uint32_t unit = CS > 1 ? ptx::cluster_id_x() : blockIdx.x;  // scheduling unit = cluster
+  const uint32_t n_units = CS > 1 ? ptx::num_clusters_x() : gridDim.x;
 
   const int64_t M = p.m_dev != nullptr ? min(p.M, (int64_t)*p.m_dev) : p.M;
   const int m_tiles = (int)((M + kBM - 1) / kBM);
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int64_t total_tiles = (int64_t)m_tiles * n_tiles;
+  const int n_units_per_row = n_tiles / CS;  // host guarantees n_tiles % CS == 0
+  const int64_t total_units = (int64_t)m_tiles * n_units_per_row;
   const int k_blocks = p.K / kBK;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_w);
+    if (Cfg::kStaged) ptx::prefetch_tensormap(&map_y);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -154,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[s], 4 * kHalves);   // one arrive per active epilogue warp
+      ptx::mbar_init(&xbar[s], 128 * kHalves * CS);  // every epilogue thread of every CTA in the cluster
     }
     ptx::fence_barrier_init();
   }
@@ -164,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -172,9 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = (int)(tile / n_tiles);
-        const int n_blk = (int)(tile % n_tiles);
+      for (int64_t u = unit; u < total_units; u += n_units) {
+        const int m_blk = (int)(u / n_units_per_row);
+        const int n_blk = (int)(u % n_units_per_row) * CS + (int)cta_rank;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -195,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t u = unit; u < total_units; u += n_units) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -223,39 +279,222 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  } else if (warp >= kCtrlWarps && (warp - kCtrlWarps) < 4 * kHalves) {
+    // ===================== epilogue =====================
+    const int e = warp - kCtrlWarps;
+    const int quad = e & 3;  // == warp & 3: the TMEM lane quadrant this warp may access
+    const int hf = e >> 2;   // which 128-column half of the accumulator tile
+    const int r_tile = quad * 32 + lane;
+    const bool issuer = (quad == 0 && lane == 0);
+    const int bar_id = 1 + hf;  // named barrier of this half (128 threads)
+    const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(hf * kGroupBytes);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = (int)(tile / n_tiles);
-      const int n_blk = (int)(tile % n_tiles);
+    uint32_t it = 0;
+    for (int64_t u = unit; u < total_units; u += n_units, ++it) {
+      const int m_blk = (int)(u / n_units_per_row);
+      const int n_blk = (int)(u % n_units_per_row) * CS + (int)cta_rank;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const int64_t row = (int64_t)m_blk * kBM + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int64_t row = (int64_t)m_blk * kBM + r_tile;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + hf * 128);
+      const int colh = n_blk * BN + hf * 128;  // first accumulator column of this half
+
+      if constexpr (Cfg::kSoftmax) {
+        // ---------- per-head softmax over Lp columns (exact statistics, three TMEM passes) ----------
+        const int lp = p.group, lv = p.group_valid;
+        const bool masked = lv < lp;
+        const bool half_ok = colh < p.N;
+        float mx[4], sm[4];
+        // pass 1: maxima
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
+            m = ok ? fmaxf(m, __uint_as_float(r[j])) : m;
+          }
+          mx[c] = m;
+        }
+        if (lp >= 64) {
+          const float a = fmaxf(mx[0], mx[1]), b = fmaxf(mx[2], mx[3]);
+          mx[0] = mx[1] = a;
+          mx[2] = mx[3] = b;
+        }
+        if (lp >= 128) {
+          const float a = fmaxf(mx[0], mx[2]);
+          mx[0] = mx[1] = mx[2] = mx[3] = a;
+        }
+        const int n_part = kHalves * CS;
+        const uint32_t parity = it & 1;
+        if (lp >= 256) {
+          // exchange across the two halves and the CTAs of the cluster through (distributed) shared memory
+          const uint32_t slot =
+              ptx::smem_u32(xbuf + (0 * 2 * kMaxCluster + (int)cta_rank * kHalves + hf) * 128 + r_tile);
+          for (int c = 0; c < CS; ++c) {
+            ptx::st_cluster_f32(ptx::map_to_cta(slot, c), mx[0]);
+            ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[0]), c));
+          }
+          ptx::mbar_wait_cluster(&xbar[0], parity);
+          float m = -INFINITY;
+          for (int q = 0; q < n_part; ++q) m = fmaxf(m, xbuf[(0 * 2 * kMaxCluster + q) * 128 + r_tile]);
+          mx[0] = mx[1] = mx[2] = mx[3] = m;
+        }
+        // pass 2: sums of exp(x - max)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          const float mb = mx[c] * kLog2e;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
+            const float ev = ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -mb));
+            s += ok ? ev : 0.f;
+          }
+          sm[c] = s;
+        }
+        if (lp >= 64) {
+          const float a = sm[0] + sm[1], b = sm[2] + sm[3];
+          sm[0] = sm[1] = a;
+          sm[2] = sm[3] = b;
+        }
+        if (lp >= 128) {
+          const float a = sm[0] + sm[2];
+          sm[0] = sm[1] = sm[2] = sm[3] = a;
+        }
+        if (lp >= 256) {
+          const uint32_t slot =
+              ptx::smem_u32(xbuf + (1 * 2 * kMaxCluster + (int)cta_rank * kHalves + hf) * 128 + r_tile);
+          for (int c = 0; c < CS; ++c) {
+            ptx::st_cluster_f32(ptx::map_to_cta(slot, c), sm[0]);
+            ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[1]), c));
+          }
+          ptx::mbar_wait_cluster(&xbar[1], parity);
+          float s = 0.f;
+          for (int q = 0; q < n_part; ++q) s += xbuf[(1 * 2 * kMaxCluster + q) * 128 + r_tile];
+          sm[0] = sm[1] = sm[2] = sm[3] = s;
+        }
+        // pass 3: probabilities -> bf16 staging -> TMA store (two 64-column groups per half)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          if (c == 3) {  // accumulator fully consumed: hand the TMEM buffer back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          }
+          const float mb = mx[c] * kLog2e;
+          const float inv = 1.0f / sm[c];
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
+            const float ev = ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -mb)) * inv;
+            v[j] = ok ? ev : 0.f;
+          }
+          if ((c & 1) == 0) {  // first chunk of a group: the staging buffer must be free again
+            if (issuer) ptx::tma_store_wait_read();
+            ptx::named_bar_sync(bar_id, 128);
+          }
+          stage_values<32>(stg, r_tile, (c & 1) * 4, v);
+          if ((c & 1) == 1) {
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(bar_id, 128);
+            if (issuer && half_ok) {
+              ptx::tma_store_2d(&map_y, staging + hf * kGroupBytes, colh + (c >> 1) * 64, m_blk * kBM);
+              ptx::tma_store_commit();
+            }
+          }
+        }
+      } else if constexpr (Cfg::kStaged) {
+        // ---------- element-wise epilogue, bf16 output through smem + TMA store ----------
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = colh + c * 32;
+          const bool active = col0 < p.N;  // uniform across the half
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          if (c == 3) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          }
+          float v[32];
+          if (active) activate_chunk<EPI>(r, p, row, col0, row_ok, v);
+          constexpr int kChunksPerGroup = kGeglu ? 4 : 2;  // accumulator chunks that fill one 64-column group
+          const int cg = c % kChunksPerGroup;
+          if (cg == 0) {
+            if (issuer) ptx::tma_store_wait_read();
+            ptx::named_bar_sync(bar_id, 128);
+          }
+          if (active) {
+            if (kGeglu)
+              stage_values<16>(stg, r_tile, cg * 2, v);
+            else
+              stage_values<32>(stg, r_tile, cg * 4, v);
+          }
+          if (cg == kChunksPerGroup - 1) {
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(bar_id, 128);
+            const int out_col = kGeglu ? (colh >> 1) : (colh + (c / 2) * 64);
+            const int n_out = kGeglu ? (p.N >> 1) : p.N;
+            if (issuer && out_col < n_out) {
+              ptx::tma_store_2d(&map_y, staging + hf * kGroupBytes, out_col, m_blk * kBM);
+              ptx::tma_store_commit();
+            }
+          }
+        }
+      } else {
+        // ---------- element-wise epilogue, fp32 output with 128-bit global stores ----------
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int col0 = n_blk * BN + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)c, r);
-        ptx::tmem_ld_wait();
-        if (row < M) epilogue_chunk<EPI, OUT_BF16>(r, p, row, col0);
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = colh + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+            activate_chunk<EPI>(r, p, row, col0, row_ok, v);
+            if (kGeglu) {
+              float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + (col0 >> 1);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (Cfg::kStaged && issuer) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still write its shared memory
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -306,35 +545,55 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols
 }
 
 template <int BN, int EPI, bool OUT_BF16>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my, const GemmParams& p,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI, OUT_BF16>;
   auto kern = gemm_tc_kernel<BN, EPI, OUT_BF16>;
   static bool attr_set = false;
   if (!attr_set) {
     NRB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int64_t tiles = ((p.M + kBM - 1) / kBM) * (int64_t)((p.N + BN - 1) / BN);
-  const int grid = (int)std::min<int64_t>(tiles, sm_count_cached());
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, p); note_launch();
+  const int cs = Cfg::kSoftmax ? p.cluster : 1;
+  const int64_t units = ((p.M + kBM - 1) / kBM) * (int64_t)(((p.N + BN - 1) / BN) / cs);
+  const int max_units = sm_count_cached() / cs;
+  const int grid = (int)std::min<int64_t>(units, max_units) * cs;
+  if (cs > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NRB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mw, my, p));
+  } else {
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, my, p);
+  }
+  note_launch();
   NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
 }
 
 template <int BN, bool OUT_BF16>
-static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& p,
-                        cudaStream_t st) {
+static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my,
+                        const GemmParams& p, cudaStream_t st) {
   switch (epi) {
     case NRB_EPI_NONE:
-      return launch_gemm<BN, NRB_EPI_NONE, OUT_BF16>(ma, mw, p, st);
+      return launch_gemm<BN, NRB_EPI_NONE, OUT_BF16>(ma, mw, my, p, st);
     case NRB_EPI_RELU:
-      return launch_gemm<BN, NRB_EPI_RELU, OUT_BF16>(ma, mw, p, st);
+      return launch_gemm<BN, NRB_EPI_RELU, OUT_BF16>(ma, mw, my, p, st);
     case NRB_EPI_EXP:
-      return launch_gemm<BN, NRB_EPI_EXP, OUT_BF16>(ma, mw, p, st);
+      return launch_gemm<BN, NRB_EPI_EXP, OUT_BF16>(ma, mw, my, p, st);
     case NRB_EPI_RESIDUAL:
-      return launch_gemm<BN, NRB_EPI_RESIDUAL, OUT_BF16>(ma, mw, p, st);
+      return launch_gemm<BN, NRB_EPI_RESIDUAL, OUT_BF16>(ma, mw, my, p, st);
     case NRB_EPI_GEGLU:
-      return launch_gemm<BN, NRB_EPI_GEGLU, OUT_BF16>(ma, mw, p, st);
+      return launch_gemm<BN, NRB_EPI_GEGLU, OUT_BF16>(ma, mw, my, p, st);
     default:
       set_error("nrb_linear(bf16): unsupported epilogue %d", epi);
       return NRB_E_INVALID;
@@ -344,7 +603,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mw, c
 // y = epi(a @ w^T + bias); a [M,K] bf16, w [N,K] bf16.
 int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
                  const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev, int N, int K,
-                 cudaStream_t st) {
+                 int group, int group_valid, cudaStream_t st) {
   NRB_REQUIRE(M > 0 && N > 0 && K > 0, "nrb_linear: empty problem");
   NRB_REQUIRE(K % kBK == 0, "nrb_linear(bf16): K must be a multiple of 64 (got %d)", K);
   NRB_REQUIRE(N % 32 == 0, "nrb_linear(bf16): N must be a multiple of 32 (got %d)", N);
@@ -356,12 +615,30 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   NRB_REQUIRE(res == nullptr || (ldres % 4 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0),
               "nrb_linear: res must be 16-byte aligned");
   NRB_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "nrb_linear: bias alignment");
-  const bool small_n = N <= 128;
-  CUtensorMap ma, mw;
+  const bool softmax = epi == NRB_EPI_SOFTMAX;
+  int cluster = 1;
+  if (softmax) {
+    NRB_REQUIRE(out_dtype == NRB_BF16, "nrb_linear: the softmax epilogue writes bf16");
+    NRB_REQUIRE(group >= 32 && (group & (group - 1)) == 0 && group <= 256 * kMaxCluster,
+                "nrb_linear: softmax group must be a power of two in [32, %d] (got %d)", 256 * kMaxCluster, group);
+    NRB_REQUIRE(group_valid >= 1 && group_valid <= group, "nrb_linear: bad softmax group_valid %d", group_valid);
+    NRB_REQUIRE(N % group == 0 && N % 256 == 0, "nrb_linear: softmax needs N %% group == 0 and N %% 256 == 0");
+    NRB_REQUIRE(bias == nullptr, "nrb_linear: softmax epilogue takes no bias");
+    cluster = group > 256 ? group / 256 : 1;
+  }
+  const bool small_n = N <= 128 && !softmax;
+  CUtensorMap ma, mw, my;
   int rc = make_tmap_bf16(&ma, a, M, K, lda, kBM);
   if (rc != NRB_OK) return rc;
   rc = make_tmap_bf16(&mw, w, N, K, ldw, small_n ? 128 : 256);
   if (rc != NRB_OK) return rc;
+  const int n_out = epi == NRB_EPI_GEGLU ? N / 2 : N;
+  if (out_dtype == NRB_BF16) {
+    rc = make_tmap_bf16(&my, y, M, n_out, ldy, kBM);
+    if (rc != NRB_OK) return rc;
+  } else {
+    my = ma;  // unused by the direct-store epilogue
+  }
   GemmParams p;
   p.M = M;
   p.m_dev = m_dev;
@@ -372,12 +649,16 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   p.ldres = ldres;
   p.y = y;
   p.ldy = ldy;
+  p.group = group;
+  p.group_valid = group_valid;
+  p.cluster = cluster;
+  if (softmax) return launch_gemm<256, NRB_EPI_SOFTMAX, true>(ma, mw, my, p, st);
   if (small_n) {
-    return out_dtype == NRB_BF16 ? dispatch_epi<128, true>(epi, ma, mw, p, st)
-                                 : dispatch_epi<128, false>(epi, ma, mw, p, st);
+    return out_dtype == NRB_BF16 ? dispatch_epi<128, true>(epi, ma, mw, my, p, st)
+                                 : dispatch_epi<128, false>(epi, ma, mw, my, p, st);
   }
-  return out_dtype == NRB_BF16 ? dispatch_epi<256, true>(epi, ma, mw, p, st)
-                               : dispatch_epi<256, false>(epi, ma, mw, p, st);
+  return out_dtype == NRB_BF16 ? dispatch_epi<256, true>(epi, ma, mw, my, p, st)
+                               : dispatch_epi<256, false>(epi, ma, mw, my, p, st);
 }
 
 }  // namespace nrb

@@ -142,7 +142,12 @@ pool_items_kernel(const float* h, int64_t ldh, const int32_t* item_off, int seq_
   }
 }
 
-static int round_up(int v, int a) { return (v + a - 1) / a * a; }
+// padded latent count: a power of two >= 32 so that softmax groups tile the 256-column MMA tiles
+static int pad_latents(int L) {
+  int p = 32;
+  while (p < L) p <<= 1;
+  return p;
+}
 
 struct FoldWs {
   float *cn, *kv, *wqT, *a32, *b32;
@@ -150,7 +155,7 @@ struct FoldWs {
 };
 static FoldWs fold_ws(void* base, int dim, int heads, int dim_head, int L) {
   const int inner = heads * dim_head;
-  const int Lp = round_up(L, 32);
+  const int Lp = pad_latents(L);
   Workspace ws(base, (size_t)-1);
   FoldWs f;
   f.cn = (float*)ws.take((size_t)L * dim * 4);
@@ -213,7 +218,7 @@ extern "C" int nrb_latent_fold(int precision, int dim, int heads, int dim_head, 
     return NRB_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  const int L = num_latents, Lp = round_up(L, 32), inner = heads * dim_head, hl = heads * Lp;
+  const int L = num_latents, Lp = pad_latents(L), inner = heads * dim_head, hl = heads * Lp;
   int rc;
   // context = LN_ctx(latents); kv = to_kv(context)            (latent_attention.py:18-19, 67)
   if ((rc = layer_norm_rows(latents, NRB_F32, dim, nullptr, ln_ctx_w, ln_ctx_b, f.cn, NRB_F32, dim, nullptr, 0, L,
@@ -264,8 +269,9 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
               "nrb_latent_forward: exactly one of pooled_out / unpooled_out must be given");
   NRB_REQUIRE(pooled_out == nullptr || token_mask != nullptr, "nrb_latent_forward: pooling needs token_mask");
   NRB_REQUIRE(w->dim % 64 == 0, "nrb_latent_forward: dim must be a multiple of 64 (got %d)", w->dim);
-  NRB_REQUIRE(w->latents_padded % 32 == 0 && w->latents_padded >= w->num_latents,
-              "nrb_latent_forward: latents_padded must be a multiple of 32");
+  NRB_REQUIRE(w->latents_padded >= 32 && (w->latents_padded & (w->latents_padded - 1)) == 0 &&
+                  w->latents_padded >= w->num_latents,
+              "nrb_latent_forward: latents_padded must be a power of two >= max(32, num_latents)");
   NRB_REQUIRE(max_tokens >= seq, "nrb_latent_forward: max_tokens (%lld) must be >= seq (%d)", (long long)max_tokens,
               seq);
   NRB_REQUIRE(w->dim <= 4096, "nrb_latent_forward: dim > 4096 unsupported");
@@ -306,13 +312,20 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
     if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, f.xres, d, rows_cap, m_dev, d,
                               st)) != NRB_OK)
       return rc;
-    // logits = xn A^T  (scale folded into A)                      :65-72
-    if ((rc = linear(P, NRB_EPI_NONE, NRB_F32, f.xn, d, w->a, d, nullptr, nullptr, 0, f.logits, hl, rows_cap, m_dev,
-                     hl, d, st)) != NRB_OK)
-      return rc;
-    if ((rc = softmax_groups(f.logits, hl, f.p, P, hl, rows_cap, m_dev, w->heads, w->latents_padded,
-                             w->num_latents, st)) != NRB_OK)
-      return rc;
+    // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
+    if (P == NRB_BF16 && hl % 256 == 0) {
+      // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
+      if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
+                       st, w->latents_padded, w->num_latents)) != NRB_OK)
+        return rc;
+    } else {
+      if ((rc = linear(P, NRB_EPI_NONE, NRB_F32, f.xn, d, w->a, d, nullptr, nullptr, 0, f.logits, hl, rows_cap,
+                       m_dev, hl, d, st)) != NRB_OK)
+        return rc;
+      if ((rc = softmax_groups(f.logits, hl, f.p, P, hl, rows_cap, m_dev, w->heads, w->latents_padded,
+                               w->num_latents, st)) != NRB_OK)
+        return rc;
+    }
     // h1 = P B^T + x                                               :74, :162
     if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, f.xres, d, f.h1, d, rows_cap, m_dev,
                      d, hl, st)) != NRB_OK)

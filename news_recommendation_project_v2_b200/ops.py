@@ -108,7 +108,8 @@ def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tens
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_NONE,
-           res: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+           res: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, group: int = 0,
+           group_valid: int = 0) -> torch.Tensor:
     """y = epilogue(a @ w.T + bias).  bf16 operands -> tcgen05, fp32 operands -> FFMA."""
     dev = require_device(a.device)
     _dev(a, "a")
@@ -126,7 +127,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         _dev(res, "res", torch.float32)
     check(load().nrb_linear(dtype_code(a.dtype), epilogue, dtype_code(out_dtype), ptr(a), a.stride(0), ptr(w),
                             w.stride(0), ptr(bias), ptr(res), res.stride(0) if res is not None else 0, ptr(y),
-                            y.stride(0), M, N, K, 0, 1.0, stream_ptr()), "nrb_linear")
+                            y.stride(0), M, N, K, group, group_valid, stream_ptr()), "nrb_linear")
     return y
 
 
@@ -179,7 +180,7 @@ def latent_fold(sd: dict, heads: int, dim_head: int, precision: torch.dtype, dev
     f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()
     lat = f32("latents")
     L, dim = lat.shape
-    Lp = (L + 31) // 32 * 32
+    Lp = max(32, 1 << (L - 1).bit_length())  # power of two: softmax groups tile the 256-column MMA tiles
     p0, p1 = "cross_attend_blocks.0.", "cross_attend_blocks.1."
     wq, wkv, wout = f32(p0 + "fn.to_q.weight"), f32(p0 + "fn.to_kv.weight"), f32(p0 + "fn.to_out.weight")
     if wq.shape != (heads * dim_head, dim):

@@ -89,3 +89,26 @@ def test_final_attention_rows_vs_oracle(ops, precision, tol):
     xb, eb = ops.final_attention_rows(table.to(precision).cuda(), w, torch.bfloat16)
     torch.testing.assert_close(xb.float().cpu().double(), want_x, atol=max(tol, 1e-2), rtol=max(tol, 1e-2))
     assert eb.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("M,N,K,group,valid", [
+    (300, 512, 128, 32, 32), (300, 512, 128, 64, 40), (257, 512, 64, 128, 128), (130, 512, 128, 128, 100),
+    (300, 512, 128, 256, 256), (300, 768, 128, 256, 130),          # group == one 256-column tile
+    (700, 1024, 256, 512, 512), (129, 4096, 768, 512, 512),        # cluster of 2 (BASELINE L=512)
+    (520, 2048, 128, 1024, 1000),                                  # cluster of 4 (BASELINE cfg 5, L=1024)
+    (200, 2048, 64, 2048, 2048),                                   # cluster of 8
+])
+def test_linear_softmax_epilogue_cluster(ops, M, N, K, group, valid):
+    """Per-group softmax fused behind the contraction; groups wider than a tile span a CTA cluster (DSMEM)."""
+    g = torch.Generator().manual_seed(M + N + K + group + valid)
+    a = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * (4.0 / math.sqrt(K))).to(torch.bfloat16)  # logits with a real spread
+    logits = (a.double() @ w.double().T).reshape(M, N // group, group)
+    logits[:, :, valid:] = -float("inf")
+    want = torch.softmax(logits, dim=-1).reshape(M, N)
+    y = ops.linear(a.cuda(), w.cuda(), None, 5, None, torch.bfloat16, group=group, group_valid=valid)
+    got = y.float().cpu().double()
+    assert torch.all(got.reshape(M, N // group, group)[:, :, valid:] == 0)
+    torch.testing.assert_close(got, want, atol=2e-3, rtol=1.0e-2)  # one bf16 rounding of p in [0,1]
+    torch.testing.assert_close(got.reshape(M, N // group, group).sum(-1), torch.ones(M, N // group, dtype=torch.float64),
+                               atol=6e-3, rtol=0)
