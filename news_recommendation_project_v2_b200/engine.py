@@ -81,16 +81,125 @@ class ScoringEngine:
 
     def __init__(self, news_embeddings: torch.Tensor, model: torch.nn.Module,
                  query_news_embeddings: Optional[torch.Tensor] = None, precision=None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, cache_table: bool = True):
+        from .latent_attention import LatentAttentionModel
+
         self.device = _lib.require_device(device)
         self.dtype = precision_dtype(precision)
         self.model = model
         self.n_rows, self.dim = news_embeddings.shape
+        self._streams = None
         with torch.cuda.device(self.device):
+            streamed = (not cache_table and not news_embeddings.is_cuda and query_news_embeddings is None
+                        and not isinstance(model, LatentAttentionModel) and news_embeddings.dtype == torch.float32)
+            if streamed:
+                self._upload_and_transform_streamed(news_embeddings)
+                return
             self.cand = resident_table(news_embeddings, self.dtype, self.device)
             src = news_embeddings if query_news_embeddings is None else query_news_embeddings
             hist_src = self.cand if query_news_embeddings is None else resident_table(src, self.dtype, self.device)
             self.prepare_user_encoder(hist_src)
+
+    # -- host table -> device tables, copy engine and tensor cores overlapped --------------------------
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._streams
+
+    def _upload_and_transform_streamed(self, table_host: torch.Tensor, chunk_rows: int = 16384) -> None:
+        """The fp32 host table crosses PCIe in row chunks on a copy stream while the previous chunk is
+        converted and pushed through the per-row FinalAttention transform on the compute stream."""
+        dev, n, d = self.device, self.n_rows, self.dim
+        s_in, _ = self._side_streams()
+        cur = torch.cuda.current_stream()
+        fp = _model_fingerprint(self.model)
+        if getattr(self, "_fa_weights_key", None) != fp:
+            self._fa_weights = _final_attention_weights(self.model, self.dtype, dev)
+            self._fa_weights_key = fp
+        self.cand = torch.empty(n, d, dtype=self.dtype, device=dev)
+        self.hist_x = torch.empty(n, d, dtype=self.dtype, device=dev)
+        self.hist_e = torch.empty(n, d, dtype=self.dtype, device=dev)
+        self.pool_mode = _lib.POOL_FINAL_ATTENTION
+        direct = self.dtype == torch.float32
+        stage = None if direct else [torch.empty(chunk_rows, d, dtype=torch.float32, device=dev) for _ in range(2)]
+        free_ev = [None, None]
+        s_in.wait_stream(cur)
+        for k, r0 in enumerate(range(0, n, chunk_rows)):
+            r1 = min(n, r0 + chunk_rows)
+            b = k & 1
+            with torch.cuda.stream(s_in):
+                if direct:
+                    self.cand[r0:r1].copy_(table_host[r0:r1], non_blocking=True)
+                else:
+                    if free_ev[b] is not None:
+                        s_in.wait_event(free_ev[b])
+                    stage[b][: r1 - r0].copy_(table_host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            cur.wait_event(ev)
+            if not direct:
+                self.cand[r0:r1].copy_(stage[b][: r1 - r0])  # fp32 -> bf16 on the device
+                free_ev[b] = torch.cuda.Event()
+                free_ev[b].record(cur)
+            ops.final_attention_rows(self.cand[r0:r1], self._fa_weights, self.dtype, x_out=self.hist_x[r0:r1],
+                                     e_out=self.hist_e[r0:r1])
+
+    def score_host(self, hist_idx: torch.Tensor, hist_off: torch.Tensor, cand_idx: torch.Tensor,
+                   cand_off: torch.Tensor, scores_out: Optional[torch.Tensor] = None,
+                   ranks_out: Optional[torch.Tensor] = None, n_chunks: int = 8):
+        """HOST (ideally pinned) CSR arrays in, HOST scores / ranks out, pipelined over impression chunks:
+        index H2D (copy stream) | fused score+rank kernel (compute stream) | result D2H (copy-out stream).
+
+        hist_idx / cand_idx int32, hist_off / cand_off int64 [I+1] CPU tensors."""
+        dev = self.device
+        n_imp = hist_off.numel() - 1
+        assert cand_off.numel() - 1 == n_imp, "Number of rows should be consistent"
+        n_h, n_c = int(hist_off[-1]), int(cand_off[-1])
+        assert n_h == hist_idx.numel() and n_c == cand_idx.numel(), \
+            "Number of impressions should match length of impression list"
+        if scores_out is None:
+            scores_out = torch.empty(n_c, dtype=torch.float32).pin_memory()
+        if ranks_out is None:
+            ranks_out = torch.empty(n_c, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(dev):
+            s_in, s_out = self._side_streams()
+            cur = torch.cuda.current_stream()
+            hi_d = torch.empty(max(n_h, 1), dtype=torch.int32, device=dev)
+            ci_d = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
+            sc_d = torch.empty(max(n_c, 1), dtype=torch.float32, device=dev)
+            rk_d = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
+            flag = ops.new_err_flag(dev)
+            ho_d = hist_off.to(dev, non_blocking=True)
+            co_d = cand_off.to(dev, non_blocking=True)
+            # impression chunks balanced by the rows they read
+            cost = 2 * hist_off.numpy() + cand_off.numpy()
+            n_chunks = max(1, min(n_chunks, n_imp))
+            cuts = np.searchsorted(cost, cost[-1] * np.arange(1, n_chunks) / n_chunks).tolist()
+            bounds = sorted(set([0] + [int(c) for c in cuts] + [n_imp]))
+            s_in.wait_stream(cur)
+            evs = []
+            for i0, i1 in zip(bounds[:-1], bounds[1:]):
+                h0, h1, c0, c1 = int(hist_off[i0]), int(hist_off[i1]), int(cand_off[i0]), int(cand_off[i1])
+                with torch.cuda.stream(s_in):
+                    hi_d[h0:h1].copy_(hist_idx[h0:h1], non_blocking=True)
+                    ci_d[c0:c1].copy_(cand_idx[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                evs.append((i0, i1, c0, c1, ev))
+            for i0, i1, c0, c1, ev in evs:
+                cur.wait_event(ev)
+                ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hi_d, ho_d[i0:i1 + 1], ci_d,
+                               co_d[i0:i1 + 1], n_c, want_ranks=True, err_flag=flag, out_scores=sc_d, out_ranks=rk_d)
+                done = torch.cuda.Event()
+                done.record(cur)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    scores_out[c0:c1].copy_(sc_d[c0:c1], non_blocking=True)
+                    ranks_out[c0:c1].copy_(rk_d[c0:c1], non_blocking=True)
+            s_out.synchronize()
+            cur.synchronize()
+            ops.raise_on_index_error(flag, "score_host")
+        return scores_out, ranks_out
 
     # -- per-row user-encoder transform (dense, once per table) --------------------------------
     def prepare_user_encoder(self, hist_src: torch.Tensor) -> None:

@@ -131,10 +131,12 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return y
 
 
-def final_attention_rows(table: torch.Tensor, weights: dict, out_dtype: torch.dtype):
+def final_attention_rows(table: torch.Tensor, weights: dict, out_dtype: torch.dtype,
+                         x_out: Optional[torch.Tensor] = None, e_out: Optional[torch.Tensor] = None):
     """Per-row FinalAttention transform: (x, exp(logit)) tables (nrb_final_attention_rows).
 
-    `weights`: linear{1..5}.weight in table.dtype, linear{1..4}.bias in fp32, on device."""
+    `weights`: linear{1..5}.weight in table.dtype, linear{1..4}.bias in fp32, on device.
+    `x_out` / `e_out`: optional preallocated [n_rows, dim] row slices to write into."""
     dev = require_device(table.device)
     _dev(table, "table")
     n_rows, dim = table.shape
@@ -146,16 +148,20 @@ def final_attention_rows(table: torch.Tensor, weights: dict, out_dtype: torch.dt
         _dev(weights[f"linear{i}.bias"], f"linear{i}.bias", torch.float32)
     lib = load()
     ws_bytes = lib.nrb_final_attention_rows_workspace_bytes(prec, n_rows, dim, hidden)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    x = torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
-    e = torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
+    ws = _workspace(dev, ws_bytes, "fa")
+    x = x_out if x_out is not None else torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
+    e = e_out if e_out is not None else torch.empty(n_rows, dim, dtype=out_dtype, device=dev)
+    for t, nm in ((x, "x_out"), (e, "e_out")):
+        _dev(t, nm, out_dtype)
+        if tuple(t.shape) != (n_rows, dim):
+            raise _lib.NrbError(f"{nm} must have shape {(n_rows, dim)}")
     check(lib.nrb_final_attention_rows(
         prec, dtype_code(out_dtype), ptr(table), table.stride(0), n_rows, dim, hidden,
         ptr(weights["linear1.weight"]), ptr(weights["linear1.bias"]),
         ptr(weights["linear2.weight"]), ptr(weights["linear2.bias"]),
         ptr(weights["linear3.weight"]), ptr(weights["linear3.bias"]),
         ptr(weights["linear4.weight"]), ptr(weights["linear4.bias"]),
-        ptr(weights["linear5.weight"]), ptr(x), ptr(e), dim, ptr(ws), ws_bytes, stream_ptr()),
+        ptr(weights["linear5.weight"]), ptr(x), ptr(e), x.stride(0), ptr(ws), ws.numel(), stream_ptr()),
         "nrb_final_attention_rows")
     return x, e
 
@@ -216,9 +222,9 @@ def latent_fold(sd: dict, heads: int, dim_head: int, precision: torch.dtype, dev
 _ws_cache: dict = {}
 
 
-def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+def _workspace(dev: torch.device, nbytes: int, tag: str = "latent") -> torch.Tensor:
     """Grow-only per-device scratch buffer (avoids cudaMalloc in the steady state)."""
-    key = (dev.index,)
+    key = (dev.index, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None

@@ -147,3 +147,28 @@ def test_latent_model_as_user_encoder():
     u = oracle.latent_pool(m.state_dict(), emb, msk, heads=2, dim_head=64)
     want = oracle.cosine_scores(u, table, imp.cand_idx, imp.cand_len).numpy()
     np.testing.assert_allclose(out["scores"], want, atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_streamed_engine_and_pipelined_host_scoring_match_resident_path(precision):
+    """ScoringEngine(cache_table=False) + score_host (copy/compute/copy-out streams, impression chunks)
+    must be bit-identical to the single-launch resident path."""
+    from news_recommendation_project_v2_b200.engine import ScoringEngine
+    dim, hidden, n_rows, n_imp = 256, 512, 40000, 3000  # > 2 table chunks of 16384 rows
+    model = _final_model(dim, hidden, 51, precision)
+    table = syn.make_table(n_rows, dim, seed=52)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand="large", seed=53)
+    ref_eng = ScoringEngine(table, model, precision=precision)
+    _, want_s, want_r = ref_eng.score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len)
+    eng = ScoringEngine(table.pin_memory(), model, precision=precision, cache_table=False)
+    assert torch.equal(eng.hist_x, ref_eng.hist_x) and torch.equal(eng.hist_e, ref_eng.hist_e)
+    assert torch.equal(eng.cand, ref_eng.cand)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    for n_chunks in (1, 3, 8):
+        s, r = eng.score_host(t(imp.hist_idx), t(syn.csr_offsets(imp.hist_len)), t(imp.cand_idx),
+                              t(syn.csr_offsets(imp.cand_len)), n_chunks=n_chunks)
+        assert s.device.type == "cpu" and torch.equal(s, want_s.cpu()) and torch.equal(r, want_r.cpu())
+    bad = imp.hist_idx.copy()
+    bad[5] = n_rows + 3
+    with pytest.raises(IndexError):
+        eng.score_host(t(bad), t(syn.csr_offsets(imp.hist_len)), t(imp.cand_idx), t(syn.csr_offsets(imp.cand_len)))
