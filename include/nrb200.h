@@ -172,6 +172,16 @@ int nrb_latent_forward(const nrb_latent_weights* w, const void* x, int x_dtype,
                        void* workspace, size_t workspace_bytes, int64_t max_tokens,
                        int64_t* n_tokens_host, nrb_stream_t stream);
 
+/* ---- MIND metrics on device (consumer of the ranks; "next" row of the hot path) ---------------
+ * replaces evaluation.py:34-98 (score_row per impression in a 4-process pool + mean):
+ * per impression AUC (tie-aware, = sklearn roc_auc_score), MRR, nDCG@5, nDCG@10 from dense ranks and
+ * integer labels with y_score = 1/rank and the reversed-stable-argsort order among tied ranks.
+ * per_imp_out: optional double [n_imp, 4] (NaN for impressions with a single class or NaN ranks);
+ * sums: double[5], ACCUMULATED (caller zeroes): sum of the four metrics over valid impressions and
+ * their count. */
+int nrb_mind_metrics(const int32_t* ranks, const int8_t* labels, const int64_t* offsets,
+                     int64_t n_imp, double* per_imp_out, double* sums, nrb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

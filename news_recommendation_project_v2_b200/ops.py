@@ -256,3 +256,20 @@ def latent_forward(fw: FoldedLatent, x: torch.Tensor, mask: Optional[torch.Tenso
     check(lib.nrb_latent_forward(C.byref(fw.struct), ptr(x), dtype_code(x.dtype), B, S, ptr(mask), pooled, unpooled,
                                  ptr(ws), ws.numel(), max_tokens, C.byref(ntok), stream_ptr()), "nrb_latent_forward")
     return out
+
+
+def mind_metrics(ranks: torch.Tensor, labels: torch.Tensor, offsets: torch.Tensor, want_per_impression: bool = True):
+    """Per-impression AUC / MRR / nDCG@5 / nDCG@10 on device (nrb_mind_metrics).
+
+    ranks int32 (dense, 0 = NaN group), labels int8, offsets int64 [I+1].
+    Returns (per_imp float64 [I,4] | None, sums float64 [5] = metric sums + number of valid impressions)."""
+    dev = require_device(ranks.device)
+    _dev(ranks, "ranks", torch.int32)
+    _dev(labels, "labels", torch.int8)
+    _dev(offsets, "offsets", torch.int64)
+    n_imp = offsets.numel() - 1
+    per = torch.empty(n_imp, 4, dtype=torch.float64, device=dev) if want_per_impression else None
+    sums = torch.zeros(5, dtype=torch.float64, device=dev)
+    check(load().nrb_mind_metrics(ptr(ranks), ptr(labels), ptr(offsets), n_imp, ptr(per), ptr(sums), stream_ptr()),
+          "nrb_mind_metrics")
+    return per, sums
