@@ -182,6 +182,15 @@ int nrb_latent_forward(const nrb_latent_weights* w, const void* x, int x_dtype,
 int nrb_mind_metrics(const int32_t* ranks, const int8_t* labels, const int64_t* offsets,
                      int64_t n_imp, double* per_imp_out, double* sums, nrb_stream_t stream);
 
+/* ---- row-sharded table: all-gather by peer stores over NVLink -----------------------------------
+ * (no reference counterpart: the reference is single GPU; BASELINE configs[4] / SURVEY.md 8e.)
+ * Writes rows [0, n_rows) of the local chunk `src` into rows dst_row_offset + r of EVERY destination
+ * in dst_ptrs_host[0..world) -- device pointers to each rank's copy of the full table, peer-mapped
+ * (symmetric memory) -- optionally converting fp32 -> bf16 on the way.  `dst_ptrs_host` is a HOST array. */
+int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride, int64_t n_rows, int dim,
+                  void* const* dst_ptrs_host, int world, int dst_dtype, int64_t dst_row_offset,
+                  int64_t dst_stride, nrb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

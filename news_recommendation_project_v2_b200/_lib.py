@@ -58,6 +58,8 @@ PROTOTYPES = {
                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _sz, _c_void_p]),
     "nrb_latent_forward_workspace_bytes": (_sz, [C.POINTER(LatentWeights), _i64]),
     "nrb_mind_metrics": (_i32, [_c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p]),
+    "nrb_push_rows": (_i32, [_c_void_p, _i32, _i64, _i64, _i32, C.POINTER(C.c_void_p), _i32, _i32, _i64, _i64,
+                             _c_void_p]),
     "nrb_latent_forward": (_i32, [C.POINTER(LatentWeights), _c_void_p, _i32, _i64, _i32, _c_void_p,
                                   _c_void_p, _c_void_p, _c_void_p, _sz, _i64, C.POINTER(_i64), _c_void_p]),
 }

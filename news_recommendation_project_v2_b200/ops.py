@@ -273,3 +273,13 @@ def mind_metrics(ranks: torch.Tensor, labels: torch.Tensor, offsets: torch.Tenso
     check(load().nrb_mind_metrics(ptr(ranks), ptr(labels), ptr(offsets), n_imp, ptr(per), ptr(sums), stream_ptr()),
           "nrb_mind_metrics")
     return per, sums
+
+
+def push_rows(src: torch.Tensor, dst_ptrs: list, dst_dtype: torch.dtype, dst_row_offset: int, dst_stride: int) -> None:
+    """All-gather building block: write the rows of `src` into every peer's full table (nrb_push_rows)."""
+    require_device(src.device)
+    _dev(src, "src")
+    n_rows, dim = src.shape
+    arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    check(load().nrb_push_rows(ptr(src), dtype_code(src.dtype), src.stride(0), n_rows, dim, arr, len(dst_ptrs),
+                               dtype_code(dst_dtype), dst_row_offset, dst_stride, stream_ptr()), "nrb_push_rows")

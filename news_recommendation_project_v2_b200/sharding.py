@@ -61,3 +61,9 @@ def reduce_sums(sums: Sequence[float], device=None) -> list:
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.tolist()
+
+
+def table_shard_bounds(n_rows: int, world: int):
+    """Row ownership of the row-sharded table: rank g owns [g*Ns, min(N, (g+1)*Ns)), Ns = ceil(N / world)."""
+    ns = (n_rows + world - 1) // world
+    return [(min(n_rows, g * ns), min(n_rows, (g + 1) * ns)) for g in range(world)]

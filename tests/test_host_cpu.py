@@ -145,3 +145,13 @@ def test_sharded_gather_gloo_world2():
         out = mgr.dict()
         mp.spawn(_gloo_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_table_shard_bounds():
+    from news_recommendation_project_v2_b200.sharding import table_shard_bounds
+    b = table_shard_bounds(10_000_000, 8)
+    assert b[0] == (0, 1_250_000) and b[-1] == (8_750_000, 10_000_000)
+    b = table_shard_bounds(40_003, 2)
+    assert b == [(0, 20_002), (20_002, 40_003)]
+    b = table_shard_bounds(5, 8)  # more ranks than rows: trailing shards are empty
+    assert b[:5] == [(i, i + 1) for i in range(5)] and all(x == (5, 5) for x in b[5:])
