@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--only-stage-a", action="store_true", help="profiling runs only: latent-attention pooling leg")
     ap.add_argument("--ref-sample", type=int, default=256, help="impressions per step of the CPU reference arm")
+    ap.add_argument("--workload", choices=["cfg4", "cfg5"], default="cfg4",
+                    help="cfg4 = headline (replicated table); cfg5 = long-history stress, row-sharded table")
+    ap.add_argument("--table-rows", type=int, default=10_000_000, help="cfg5: total table rows")
+    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p", help="cfg5: all-gather implementation")
     return ap.parse_args()
 
 
@@ -397,10 +401,113 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def run_sharded(args):
+    """BASELINE configs[4]: history <= 200, d=1024, 1024 latents (latent-attention user encoder), table
+    row-sharded over the ranks: step = per-shard row transform + peer-store all-gather + local scoring."""
+    import torch.distributed as dist
+
+    from news_recommendation_project_v2_b200 import _lib, ops
+    from news_recommendation_project_v2_b200.latent_attention import LatentAttentionModel
+    from news_recommendation_project_v2_b200.sharded import ShardedTableEngine
+    from news_recommendation_project_v2_b200.sharding import table_shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device(dev)
+    if not dist.is_initialized():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            os.environ.setdefault("RANK", "0")
+            os.environ.setdefault("WORLD_SIZE", "1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = measured_peaks()
+    d, L, h_max, n_rows = 1024, 1024, 200, args.table_rows
+    n_imp = max(1, 1_048_576 // world) if args.impressions == 2_400_000 else args.impressions
+    model = LatentAttentionModel(dim=d, num_latents=L, precision="bf16").eval()
+    model.load_state_dict(syn.make_latent_state_dict(d, L, seed=1234))
+    model.to(dev)
+    r0, r1 = table_shard_bounds(n_rows, world)[rank]
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    local_rows = torch.nn.functional.normalize(
+        torch.randn(r1 - r0, d, generator=g, device=dev, dtype=torch.float32), dim=-1).to(torch.bfloat16)
+    hist_idx, h_off, cand_idx, c_off, _, _, n_h, n_c = make_device_impressions(n_imp, n_rows, h_max, 1234 + rank, dev)
+    eng = ShardedTableEngine(local_rows, n_rows, model, precision="bf16", device=dev, gather=args.gather)
+    scores = torch.empty(n_c, dtype=torch.float32, device=dev)
+    ranks = torch.empty(n_c, dtype=torch.int32, device=dev)
+    flag = ops.new_err_flag(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        eng.build(local_rows)
+        if evs:
+            evs[1].record()
+        eng.score_device(hist_idx, h_off, cand_idx, c_off, n_c, want_ranks=True, err_flag=flag, out_scores=scores,
+                         out_ranks=ranks)
+        if evs:
+            evs[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    launches0 = lib.nrb_kernel_launches()
+    kev = [(ev(), ev(), ev()) for _ in range(args.steps)]
+    t0, t1 = ev(), ev()
+    t0.record()
+    for i in range(args.steps):
+        step(kev[i])
+    t1.record()
+    barrier()
+    launches = lib.nrb_kernel_launches() - launches0
+    ops.raise_on_index_error(flag, "bench")
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    build_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in kev]))
+    score_ms = float(np.mean([b.elapsed_time(c) for _, b, c in kev]))
+    f_row = 4 * 8 * d * L + 24 * d * d  # executed FLOPs per row (folded heads)
+    f_row_ref = 4 * d * 4096 + 4 * 4096 * L + 24 * d * d
+    alg_bytes = (n_h + n_c) * d * 2 + 4 * (n_h + n_c) + 8 * n_c
+    out = {
+        "metric": METRIC, "value": round(n_imp * world / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "long-history stress (BASELINE configs[4]): latent-attention user encoder, table "
+                               "row-sharded, per-shard transform + all-gather (%s) + gather/pool/cosine/rank" % args.gather,
+                   "table_rows": n_rows, "rows_per_gpu": r1 - r0, "impressions_per_gpu": n_imp, "dim": d, "latents": L,
+                   "history_max": h_max, "sum_history": n_h, "sum_candidates": n_c},
+        "gpu_launches": int(launches),
+        "build": {"ms": round(build_ms, 3),
+                  "tflops_executed": round((r1 - r0) * f_row / (build_ms * 1e-3) / 1e12, 1),
+                  "tflops_reference_formulation": round((r1 - r0) * f_row_ref / (build_ms * 1e-3) / 1e12, 1),
+                  "allgather_bytes_in_per_gpu": int(2 * (n_rows - (r1 - r0)) * d * 2)},
+        "roofline": {"bound": "hbm", "kernel": "score_rank_kernel", "achieved": round(alg_bytes / (score_ms * 1e-3) / 1e9, 1),
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(alg_bytes / (score_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                     "traffic": None, "kernel_ms": round(score_ms, 3)},
+    }
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_sharded(args)
     else:
         run_native(args)
 

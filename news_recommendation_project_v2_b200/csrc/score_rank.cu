@@ -75,7 +75,7 @@ __device__ __forceinline__ void load_row(const char* base, int lane, uint4 (&v)[
 }
 
 template <typename T, int NV, int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 score_rank_kernel(const ScoreRankParams p) {
   constexpr int EPV = Vec16<T>::EPV;
   constexpr int EPL = NV * EPV;  // elements owned by one lane
@@ -100,6 +100,11 @@ score_rank_kernel(const ScoreRankParams p) {
     }
 
     // ---- history: gather rows, accumulate in registers -------------------------------
+    // HR rows (x MODE-0's two tables) are requested back to back and only then consumed: the
+    // __syncwarp() between the loads and their first use keeps ptxas from interleaving
+    // load -> use -> load (which leaves 1-2 requests in flight per lane and is latency bound).
+    constexpr int kTables = MODE == NRB_POOL_FINAL_ATTENTION ? 2 : 1;
+    constexpr int HR = (16 / (NV * kTables)) > 0 ? (16 / (NV * kTables)) : 1;  // ~16 requests of 16 B per lane
     for (int64_t base = h0; base < h1; base += 32) {
       const int cnt = (int)min((int64_t)32, h1 - base);
       int my = 0;
@@ -110,56 +115,38 @@ score_rank_kernel(const ScoreRankParams p) {
           my = 0;
         }
       }
-      for (int s = 0; s < cnt; s += 2) {
-        const bool two = (s + 1 < cnt);  // warp-uniform
-        const int r0 = __shfl_sync(kFullMask, my, s);
-        const int r1 = __shfl_sync(kFullMask, my, two ? s + 1 : s);
-        uint4 x0[NV], x1[NV];
-        load_row<T, NV>(p.hist_x + (int64_t)r0 * p.hist_stride_bytes, lane, x0);
-        load_row<T, NV>(p.hist_x + (int64_t)r1 * p.hist_stride_bytes, lane, x1);
-        if (MODE == NRB_POOL_FINAL_ATTENTION) {
-          uint4 e0[NV], e1[NV];
-          load_row<T, NV>(p.hist_e + (int64_t)r0 * p.hist_stride_bytes, lane, e0);
-          load_row<T, NV>(p.hist_e + (int64_t)r1 * p.hist_stride_bytes, lane, e1);
+      for (int s = 0; s < cnt; s += HR) {
+        uint4 x[HR][NV];
+        uint4 e[MODE == NRB_POOL_FINAL_ATTENTION ? HR : 1][NV];
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            float xf[EPV], ef[EPV];
-            Vec16<T>::unpack(x0[i], xf);
-            Vec16<T>::unpack(e0[i], ef);
+        for (int q = 0; q < HR; ++q) {
+          // past the end: re-request the last valid row (an L2 hit, ignored below) so that the loads
+          // stay unconditional
+          const int r = __shfl_sync(kFullMask, my, min(s + q, cnt - 1));
+          load_row<T, NV>(p.hist_x + (int64_t)r * p.hist_stride_bytes, lane, x[q]);
+          if (MODE == NRB_POOL_FINAL_ATTENTION)
+            load_row<T, NV>(p.hist_e + (int64_t)r * p.hist_stride_bytes, lane, e[q]);
+        }
+        __syncwarp();
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) {
-              num[i * EPV + k] = fmaf(xf[k], ef[k], num[i * EPV + k]);
-              den[i * EPV + k] += ef[k];
-            }
-          }
-          if (two) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-              float xf[EPV], ef[EPV];
-              Vec16<T>::unpack(x1[i], xf);
-              Vec16<T>::unpack(e1[i], ef);
-#pragma unroll
-              for (int k = 0; k < EPV; ++k) {
-                num[i * EPV + k] = fmaf(xf[k], ef[k], num[i * EPV + k]);
-                den[i * EPV + k] += ef[k];
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            float xf[EPV];
-            Vec16<T>::unpack(x0[i], xf);
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) num[i * EPV + k] += xf[k];
-          }
-          if (two) {
+        for (int q = 0; q < HR; ++q) {
+          if (s + q < cnt) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
               float xf[EPV];
-              Vec16<T>::unpack(x1[i], xf);
+              Vec16<T>::unpack(x[q][i], xf);
+              if (MODE == NRB_POOL_FINAL_ATTENTION) {
+                float ef[EPV];
+                Vec16<T>::unpack(e[q][i], ef);
 #pragma unroll
-              for (int k = 0; k < EPV; ++k) num[i * EPV + k] += xf[k];
+                for (int k = 0; k < EPV; ++k) {
+                  num[i * EPV + k] = fmaf(xf[k], ef[k], num[i * EPV + k]);
+                  den[i * EPV + k] += ef[k];
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) num[i * EPV + k] += xf[k];
+              }
             }
           }
         }
@@ -219,38 +206,44 @@ score_rank_kernel(const ScoreRankParams p) {
         }
       }
       float my_score = 0.f;
-      for (int s = 0; s < cnt; s += 2) {
-        const bool two = (s + 1 < cnt);
-        const int r0 = __shfl_sync(kFullMask, my, s);
-        const int r1 = __shfl_sync(kFullMask, my, two ? s + 1 : s);
-        uint4 a0[NV], a1[NV];
-        load_row<T, NV>(p.cand + (int64_t)r0 * p.cand_stride_bytes, lane, a0);
-        load_row<T, NV>(p.cand + (int64_t)r1 * p.cand_stride_bytes, lane, a1);
-        float d0 = 0.f, q0 = 0.f, d1 = 0.f, q1 = 0.f;
+      constexpr int CR = (16 / NV) > 0 ? (16 / NV) : 1;  // candidate rows in flight per iteration
+      for (int s = 0; s < cnt; s += CR) {
+        uint4 a[CR][NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          float f0[EPV], f1[EPV];
-          Vec16<T>::unpack(a0[i], f0);
-          Vec16<T>::unpack(a1[i], f1);
+        for (int q = 0; q < CR; ++q) {
+          const int r = __shfl_sync(kFullMask, my, min(s + q, cnt - 1));
+          load_row<T, NV>(p.cand + (int64_t)r * p.cand_stride_bytes, lane, a[q]);
+        }
+        __syncwarp();  // all loads issued before the first use (see the history loop)
+        float dot[CR], sq[CR];
 #pragma unroll
-          for (int k = 0; k < EPV; ++k) {
-            d0 = fmaf(f0[k], num[i * EPV + k], d0);
-            q0 = fmaf(f0[k], f0[k], q0);
-            d1 = fmaf(f1[k], num[i * EPV + k], d1);
-            q1 = fmaf(f1[k], f1[k], q1);
+        for (int q = 0; q < CR; ++q) {
+          dot[q] = 0.f;
+          sq[q] = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            float f[EPV];
+            Vec16<T>::unpack(a[q][i], f);
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) {
+              dot[q] = fmaf(f[k], num[i * EPV + k], dot[q]);
+              sq[q] = fmaf(f[k], f[k], sq[q]);
+            }
           }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          d0 += __shfl_xor_sync(kFullMask, d0, o);
-          q0 += __shfl_xor_sync(kFullMask, q0, o);
-          d1 += __shfl_xor_sync(kFullMask, d1, o);
-          q1 += __shfl_xor_sync(kFullMask, q1, o);
+#pragma unroll
+          for (int q = 0; q < CR; ++q) {
+            dot[q] += __shfl_xor_sync(kFullMask, dot[q], o);
+            sq[q] += __shfl_xor_sync(kFullMask, sq[q], o);
+          }
         }
-        const float sc0 = d0 / fmaxf(sqrtf(q0), 1e-8f);
-        const float sc1 = d1 / fmaxf(sqrtf(q1), 1e-8f);
-        if (lane == s) my_score = sc0;
-        if (two && lane == s + 1) my_score = sc1;
+#pragma unroll
+        for (int q = 0; q < CR; ++q) {
+          const float sc = dot[q] / fmaxf(sqrtf(sq[q]), 1e-8f);
+          if (lane == s + q) my_score = sc;
+        }
       }
       if (lane < cnt) {
         p.scores[base + lane] = my_score;

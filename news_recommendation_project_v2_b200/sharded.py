@@ -43,30 +43,45 @@ class ShardedTableEngine(ScoringEngine):
         if local_rows.shape[0] != r1 - r0:
             raise _lib.NrbError(f"rank {self.rank} must hold rows [{r0},{r1}) = {r1 - r0} rows, got {local_rows.shape[0]}")
         latent = isinstance(model, LatentAttentionModel)
+        self._latent = latent
         self.pool_mode = _lib.POOL_MEAN_L2 if latent else _lib.POOL_FINAL_ATTENTION
+        self.gather, self.chunk_rows = gather, chunk_rows
+        self._bounds = (r0, r1)
         n, d, dev = self.n_rows, self.dim, self.device
         with torch.cuda.device(dev):
-            names = ["cand", "hist_x"] + ([] if latent else ["hist_e"])
+            self._names = ["cand", "hist_x"] + ([] if latent else ["hist_e"])
             if gather == "p2p":
                 import torch.distributed._symmetric_memory as symm_mem
 
-                full, ptrs = {}, {}
-                for nm in names:
+                self._full, self._ptrs = {}, {}
+                for nm in self._names:
                     t = symm_mem.empty((n, d), dtype=self.dtype, device=dev)
                     h = symm_mem.rendezvous(t, self.group)
-                    full[nm], ptrs[nm] = t, list(h.buffer_ptrs)
+                    self._full[nm], self._ptrs[nm] = t, list(h.buffer_ptrs)
             elif gather == "nccl":
                 ns = table_shard_bounds(n, self.world)[0][1]
-                full = {nm: torch.empty(self.world * ns, d, dtype=self.dtype, device=dev) for nm in names}
-                ptrs = None
+                self._full = {nm: torch.empty(self.world * ns, d, dtype=self.dtype, device=dev) for nm in self._names}
+                self._ptrs = None
             else:
                 raise ValueError(gather)
+        self.build(local_rows)
+
+    def build(self, local_rows: torch.Tensor) -> None:
+        """Transform this rank's shard chunk by chunk and all-gather the chunks (collective: every rank calls it)."""
+        r0, r1 = self._bounds
+        n, d, dev = self.n_rows, self.dim, self.device
+        latent, names, full, ptrs = self._latent, self._names, self._full, self._ptrs
+        ns = table_shard_bounds(n, self.world)[0][1]
+        with torch.cuda.device(dev):
+            # nobody may still be scoring against the previous contents when peers start overwriting them
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)
             if latent:
-                fw = model.folded(self.dtype, dev)
+                fw = self.model.folded(self.dtype, dev)
             else:
-                w = _final_attention_weights(model, self.dtype, dev)
-            for c0 in range(0, r1 - r0, chunk_rows):
-                c1 = min(r1 - r0, c0 + chunk_rows)
+                w = _final_attention_weights(self.model, self.dtype, dev)
+            for c0 in range(0, r1 - r0, self.chunk_rows):
+                c1 = min(r1 - r0, c0 + self.chunk_rows)
                 chunk = local_rows[c0:c1].to(dev, non_blocking=True)
                 chunk = chunk.to(self.dtype).contiguous()
                 if latent:
@@ -85,9 +100,8 @@ class ShardedTableEngine(ScoringEngine):
                 for nm in names:
                     dist.all_gather_into_tensor(full[nm], full[nm][self.rank * ns:(self.rank + 1) * ns].clone(),
                                                 group=self.group)
-                    full[nm] = full[nm][:n]
             # every rank's pushes have landed before anybody scores
             torch.cuda.current_stream().synchronize()
             dist.barrier(group=self.group)
-            self.cand, self.hist_x = full["cand"], full["hist_x"]
-            self.hist_e = None if latent else full["hist_e"]
+            self.cand, self.hist_x = full["cand"][:n], full["hist_x"][:n]
+            self.hist_e = None if latent else full["hist_e"][:n]
