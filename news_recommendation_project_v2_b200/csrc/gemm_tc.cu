@@ -50,7 +50,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kStaged ? kHalves * kGroupBytes : 0;
-  static constexpr int kXchgBytes = kSoftmax ? 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [step][participant][row]
+  static constexpr int kXchgBytes = kSoftmax ? 2 * 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [parity][m|s][participant][row]
   static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXchgBytes;
   static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
@@ -92,13 +92,13 @@ constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float gelu_erf_fast(float g) {
   const float z = fabsf(g) * 0.70710678118654752440f;
   const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * ex2_approx(-z * z * kLog2e);  // 0.5 * erfc(|z|)
-  const float cdf = g >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return g * cdf;
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float half_erfc = p * t * ex2_approx(z * (z * -kLog2e));  // 0.5 * erfc(|z|)
+  // g * Phi(g) = relu(g) - |g| * half_erfc  (g >= 0: g(1-h); g < 0: g*h) -- no select, no cancellation
+  return fmaf(-fabsf(g), half_erfc, fmaxf(g, 0.f));
 }
 
 // ---- shared epilogue math: 32 accumulator columns of one row -> post-activation fp32 values -------------
@@ -302,87 +302,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int colh = n_blk * BN + hf * 128;  // first accumulator column of this half
 
       if constexpr (Cfg::kSoftmax) {
-        // ---------- per-head softmax over Lp columns (exact statistics, three TMEM passes) ----------
+        // ---------- per-head softmax over Lp columns: two TMEM passes + ONE statistics exchange ----------
+        // pass A: per 32-column chunk (m_c, s_c = sum exp(x - m_c)); chunks merged to the group in registers;
+        //         groups wider than this warp's 128 columns merge the (m, s) pairs of all participants
+        //         (the other half of this CTA and the other CTAs of the cluster) through DSMEM.
+        // pass B: p = 2^(x*log2e - (M*log2e + log2 S)): normalised in the exponent, one bf16 rounding.
         const int lp = p.group, lv = p.group_valid;
         const bool masked = lv < lp;
         const bool half_ok = colh < p.N;
         float mx[4], sm[4];
-        // pass 1: maxima
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
-          float m = -INFINITY;
+          float xv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
-            m = ok ? fmaxf(m, __uint_as_float(r[j])) : m;
+            xv[j] = ok ? __uint_as_float(r[j]) : -INFINITY;
           }
+          float m = xv[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, xv[j]);
+          const float mb = (m == -INFINITY ? 0.f : m) * kLog2e;  // an all-masked chunk contributes nothing
+          float sacc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sacc += ex2_approx(fmaf(xv[j], kLog2e, -mb));
           mx[c] = m;
+          sm[c] = sacc;
         }
+        // merge (m, s) pairs: s_total = sum_c s_c * 2^((m_c - m) log2e)
+        auto merge2 = [](float& ma, float& sa, float mb_, float sb_) {
+          const float m = fmaxf(ma, mb_);
+          const float ms = (m == -INFINITY ? 0.f : m);
+          sa = sa * ex2_approx((ma - ms) * kLog2e) + sb_ * ex2_approx((mb_ - ms) * kLog2e);
+          ma = m;
+        };
         if (lp >= 64) {
-          const float a = fmaxf(mx[0], mx[1]), b = fmaxf(mx[2], mx[3]);
-          mx[0] = mx[1] = a;
-          mx[2] = mx[3] = b;
+          merge2(mx[0], sm[0], mx[1], sm[1]);
+          merge2(mx[2], sm[2], mx[3], sm[3]);
+          mx[1] = mx[0];
+          sm[1] = sm[0];
+          mx[3] = mx[2];
+          sm[3] = sm[2];
         }
         if (lp >= 128) {
-          const float a = fmaxf(mx[0], mx[2]);
-          mx[0] = mx[1] = mx[2] = mx[3] = a;
+          merge2(mx[0], sm[0], mx[2], sm[2]);
+          mx[1] = mx[2] = mx[3] = mx[0];
+          sm[1] = sm[2] = sm[3] = sm[0];
         }
-        const int n_part = kHalves * CS;
-        const uint32_t parity = it & 1;
         if (lp >= 256) {
-          // exchange across the two halves and the CTAs of the cluster through (distributed) shared memory
-          const uint32_t slot =
-              ptx::smem_u32(xbuf + (0 * 2 * kMaxCluster + (int)cta_rank * kHalves + hf) * 128 + r_tile);
+          const int n_part = kHalves * CS;
+          const uint32_t parity = it & 1;
+          const int me = (int)cta_rank * kHalves + hf;
+          // slots are double buffered by tile parity: a peer can reuse buffer `parity` only two tiles later,
+          // which requires this thread's arrival at the next exchange, i.e. after it has read these slots
+          float* xb = xbuf + parity * (2 * 2 * kMaxCluster * 128);
+          const uint32_t slot_m = ptx::smem_u32(xb + (0 * 2 * kMaxCluster + me) * 128 + r_tile);
+          const uint32_t slot_s = ptx::smem_u32(xb + (1 * 2 * kMaxCluster + me) * 128 + r_tile);
           for (int c = 0; c < CS; ++c) {
-            ptx::st_cluster_f32(ptx::map_to_cta(slot, c), mx[0]);
+            ptx::st_cluster_f32(ptx::map_to_cta(slot_m, c), mx[0]);
+            ptx::st_cluster_f32(ptx::map_to_cta(slot_s, c), sm[0]);
             ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[0]), c));
           }
           ptx::mbar_wait_cluster(&xbar[0], parity);
           float m = -INFINITY;
-          for (int q = 0; q < n_part; ++q) m = fmaxf(m, xbuf[(0 * 2 * kMaxCluster + q) * 128 + r_tile]);
+          for (int q = 0; q < n_part; ++q) m = fmaxf(m, xb[(0 * 2 * kMaxCluster + q) * 128 + r_tile]);
+          float st = 0.f;
+          for (int q = 0; q < n_part; ++q)
+            st += xb[(1 * 2 * kMaxCluster + q) * 128 + r_tile] *
+                  ex2_approx((xb[(0 * 2 * kMaxCluster + q) * 128 + r_tile] - m) * kLog2e);
           mx[0] = mx[1] = mx[2] = mx[3] = m;
+          sm[0] = sm[1] = sm[2] = sm[3] = st;
         }
-        // pass 2: sums of exp(x - max)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
-          ptx::tmem_ld_wait();
-          const float mb = mx[c] * kLog2e;
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
-            const float ev = ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -mb));
-            s += ok ? ev : 0.f;
-          }
-          sm[c] = s;
-        }
-        if (lp >= 64) {
-          const float a = sm[0] + sm[1], b = sm[2] + sm[3];
-          sm[0] = sm[1] = a;
-          sm[2] = sm[3] = b;
-        }
-        if (lp >= 128) {
-          const float a = sm[0] + sm[2];
-          sm[0] = sm[1] = sm[2] = sm[3] = a;
-        }
-        if (lp >= 256) {
-          const uint32_t slot =
-              ptx::smem_u32(xbuf + (1 * 2 * kMaxCluster + (int)cta_rank * kHalves + hf) * 128 + r_tile);
-          for (int c = 0; c < CS; ++c) {
-            ptx::st_cluster_f32(ptx::map_to_cta(slot, c), sm[0]);
-            ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[1]), c));
-          }
-          ptx::mbar_wait_cluster(&xbar[1], parity);
-          float s = 0.f;
-          for (int q = 0; q < n_part; ++q) s += xbuf[(1 * 2 * kMaxCluster + q) * 128 + r_tile];
-          sm[0] = sm[1] = sm[2] = sm[3] = s;
-        }
-        // pass 3: probabilities -> bf16 staging -> TMA store (two 64-column groups per half)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -393,14 +386,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
           }
-          const float mb = mx[c] * kLog2e;
-          const float inv = 1.0f / sm[c];
+          const float shift = fmaf(mx[c], kLog2e, __log2f(sm[c]));  // M*log2e + log2 S
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
-            const float ev = ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -mb)) * inv;
-            v[j] = ok ? ev : 0.f;
+            v[j] = ok ? ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -shift)) : 0.f;
           }
           if ((c & 1) == 0) {  // first chunk of a group: the staging buffer must be free again
             if (issuer) ptx::tma_store_wait_read();
