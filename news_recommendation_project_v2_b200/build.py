@@ -53,6 +53,9 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = nvcc_path()
+    extra = os.environ.get("NRB200_NVCC_EXTRA", "").split()  # experiments only (e.g. -DNRB_MAX_STAGES=3)
+    if extra:
+        force = True
     hdrs = headers()
     jobs = []
     for src in sources():
@@ -62,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:

@@ -53,7 +53,10 @@ struct GemmCfg {
   static constexpr int kXchgBytes = kSoftmax ? 2 * 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [parity][m|s][participant][row]
   static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXchgBytes;
   static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+#ifndef NRB_MAX_STAGES
+#define NRB_MAX_STAGES 6
+#endif
+  static constexpr int kStages = kStagesRaw > NRB_MAX_STAGES ? NRB_MAX_STAGES : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static_assert(kStages >= 2, "pipeline too shallow");
@@ -209,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 4 * kHalves);   // one arrive per active epilogue warp
-      ptx::mbar_init(&xbar[s], 128 * kHalves * CS);  // every epilogue thread of every CTA in the cluster
+      ptx::mbar_init(&xbar[s], 4 * kHalves * CS);    // one arrive per epilogue warp of every CTA in the cluster
     }
     ptx::fence_barrier_init();
   }
@@ -311,26 +314,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool masked = lv < lp;
         const bool half_ok = colh < p.N;
         float mx[4], sm[4];
+        uint32_t rbuf[2][32];
+        ptx::tmem_ld_32x32(taddr, rbuf[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
+          if (c + 1 < 4) ptx::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);  // prefetch
+          const uint32_t(&r)[32] = rbuf[c & 1];
           float xv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
             xv[j] = ok ? __uint_as_float(r[j]) : -INFINITY;
           }
-          float m = xv[0];
+          float m4[4] = {xv[0], xv[1], xv[2], xv[3]};  // 4 independent chains instead of one of length 32
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, xv[j]);
+          for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], xv[j]);
+          const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           const float mb = (m == -INFINITY ? 0.f : m) * kLog2e;  // an all-masked chunk contributes nothing
-          float sacc = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sacc += ex2_approx(fmaf(xv[j], kLog2e, -mb));
+          for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_approx(fmaf(xv[j], kLog2e, -mb));
           mx[c] = m;
-          sm[c] = sacc;
+          sm[c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         }
         // merge (m, s) pairs: s_total = sum_c s_c * 2^((m_c - m) log2e)
         auto merge2 = [](float& ma, float& sa, float mb_, float sb_) {
@@ -364,8 +370,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int c = 0; c < CS; ++c) {
             ptx::st_cluster_f32(ptx::map_to_cta(slot_m, c), mx[0]);
             ptx::st_cluster_f32(ptx::map_to_cta(slot_s, c), sm[0]);
-            ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[0]), c));
           }
+          // one release-arrive per warp and destination: the lanes' stores are ordered before it by
+          // __syncwarp (cta scope) and made visible cluster-wide by the cumulative release
+          __syncwarp();
+          if (lane == 0)
+            for (int c = 0; c < CS; ++c) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[0]), c));
           ptx::mbar_wait_cluster(&xbar[0], parity);
           float m = -INFINITY;
           for (int q = 0; q < n_part; ++q) m = fmaxf(m, xb[(0 * 2 * kMaxCluster + q) * 128 + r_tile]);
@@ -376,11 +386,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mx[0] = mx[1] = mx[2] = mx[3] = m;
           sm[0] = sm[1] = sm[2] = sm[3] = st;
         }
+        ptx::tmem_ld_32x32(taddr, rbuf[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
+          if (c + 1 < 4) ptx::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);  // prefetch
+          const uint32_t(&r)[32] = rbuf[c & 1];
           if (c == 3) {  // accumulator fully consumed: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
@@ -409,13 +420,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       } else if constexpr (Cfg::kStaged) {
         // ---------- element-wise epilogue, bf16 output through smem + TMA store ----------
+        uint32_t rbuf[2][32];
+        ptx::tmem_ld_32x32(taddr, rbuf[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int col0 = colh + c * 32;
           const bool active = col0 < p.N;  // uniform across the half
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
+          if (c + 1 < 4) ptx::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);  // prefetch
+          const uint32_t(&r)[32] = rbuf[c & 1];
           if (c == 3) {
             ptx::tc_fence_before();
             __syncwarp();
