@@ -152,6 +152,8 @@ def run_native(args):
     dev = torch.device("cuda", local)
     _lib.require_device(dev)
     if world > 1:
+        # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints its banner on stdout)
+        os.environ["NCCL_DEBUG"] = os.environ.get("NRB200_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = measured_peaks()

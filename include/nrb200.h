@@ -115,6 +115,11 @@ int nrb_linear(int precision, int epilogue, int out_dtype,
                const float* res, int64_t ldres, void* y, int64_t ldy,
                int64_t M, int N, int K, int group, int group_valid, nrb_stream_t stream);
 
+/* y = LayerNorm(x) * gamma + beta over the last dimension (biased variance, eps inside the sqrt):
+ * torch.nn.LayerNorm at latent_attention.py:10-19 (eps 1e-5) and attention.py:170-171,193 (eps 1e-12). */
+int nrb_layer_norm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                   void* y, int y_dtype, int64_t ldy, int64_t rows, int dim, nrb_stream_t stream);
+
 /* ---- FinalAttention per-row transform -------------------------------------------------
  * replaces the per-history-slot MLPs of modeling_utils.py:218-222 by one pass over the
  * table (they depend only on the news row):

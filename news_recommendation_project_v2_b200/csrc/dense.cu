@@ -26,7 +26,7 @@ __device__ __forceinline__ void store_elem(void* p, int dt, int64_t i, float v) 
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,
                   const float* beta, void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy,
-                  int64_t rows, const int* rows_dev, int dim) {
+                  int64_t rows, const int* rows_dev, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -42,7 +42,7 @@ layer_norm_kernel(const void* x, int x_dtype, int64_t ldx, const int32_t* row_ma
       const float d = load_elem(x, x_dtype, xo + i) - mean;
       q = fmaf(d, d, q);
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)dim + 1e-5f);
+    const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
     for (int i = lane; i < dim; i += 32) {
       const float v = load_elem(x, x_dtype, xo + i);
       store_elem(y, y_dtype, r * ldy + i, (v - mean) * rstd * gamma[i] + beta[i]);
@@ -53,12 +53,12 @@ layer_norm_kernel(const void* x, int x_dtype, int64_t ldx, const int32_t* row_ma
 
 int layer_norm_rows(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,
                     const float* beta, void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy,
-                    int64_t rows, const int* rows_dev, int dim, cudaStream_t st) {
+                    int64_t rows, const int* rows_dev, int dim, cudaStream_t st, float eps) {
   if (rows <= 0) return NRB_OK;
   const int64_t want = (rows + 7) / 8;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 16);
   layer_norm_kernel<<<grid, 256, 0, st>>>(x, x_dtype, ldx, row_map, gamma, beta, y, y_dtype, ldy, copy_f32, ldcopy,
-                                          rows, rows_dev, dim); note_launch();
+                                          rows, rows_dev, dim, eps); note_launch();
   NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
 }
@@ -180,6 +180,16 @@ constexpr int64_t kFaChunkRows = 16384;
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_layer_norm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                              void* y, int y_dtype, int64_t ldy, int64_t rows, int dim, nrb_stream_t stream) {
+  NRB_REQUIRE(x && gamma && beta && y, "nrb_layer_norm: null pointer");
+  NRB_REQUIRE((x_dtype == NRB_F32 || x_dtype == NRB_BF16) && (y_dtype == NRB_F32 || y_dtype == NRB_BF16),
+              "nrb_layer_norm: bad dtype");
+  NRB_REQUIRE(rows >= 0 && dim > 0 && eps >= 0.f, "nrb_layer_norm: bad sizes");
+  return layer_norm_rows(x, x_dtype, ldx, nullptr, gamma, beta, y, y_dtype, ldy, nullptr, 0, rows, nullptr, dim,
+                         as_stream(stream), eps);
+}
 
 extern "C" int nrb_linear(int precision, int epilogue, int out_dtype, const void* a, int64_t lda, const void* w,
                           int64_t ldw, const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy,

@@ -22,7 +22,7 @@ int linear(int precision, int epi, int out_dtype, const void* a, int64_t lda, co
 // dense.cu -- row-wise helpers (all take an optional device-side row count)
 int layer_norm_rows(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,
                     const float* beta, void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy,
-                    int64_t rows, const int* rows_dev, int dim, cudaStream_t st);
+                    int64_t rows, const int* rows_dev, int dim, cudaStream_t st, float eps = 1e-5f);
 int softmax_groups(const float* logits, int64_t ldl, void* p, int p_dtype, int64_t ldp, int64_t rows,
                    const int* rows_dev, int n_groups, int group, int valid, cudaStream_t st);
 int convert_rows(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows,

@@ -90,8 +90,10 @@ class ScoringEngine:
         self.n_rows, self.dim = news_embeddings.shape
         self._streams = None
         with torch.cuda.device(self.device):
+            from .attention import NewAttention
             streamed = (not cache_table and not news_embeddings.is_cuda and query_news_embeddings is None
-                        and not isinstance(model, LatentAttentionModel) and news_embeddings.dtype == torch.float32)
+                        and not isinstance(model, (LatentAttentionModel, NewAttention))
+                        and news_embeddings.dtype == torch.float32)
             if streamed:
                 self._upload_and_transform_streamed(news_embeddings)
                 return
@@ -203,9 +205,14 @@ class ScoringEngine:
 
     # -- per-row user-encoder transform (dense, once per table) --------------------------------
     def prepare_user_encoder(self, hist_src: torch.Tensor) -> None:
+        from .attention import NewAttention
         from .latent_attention import LatentAttentionModel
 
-        if isinstance(self.model, LatentAttentionModel):
+        if isinstance(self.model, NewAttention):
+            # LayerNorm chain + exp(linear1): per-row, same exp-weighted pooling as FinalAttention
+            self.hist_x, self.hist_e = self.model.row_tables(hist_src, self.dtype)
+            self.pool_mode = _lib.POOL_FINAL_ATTENTION
+        elif isinstance(self.model, LatentAttentionModel):
             # tokens are independent: run the block once per table row, then mean-pool
             fw = self.model.folded(self.dtype, self.device)
             rows = ops.latent_forward(fw, hist_src.view(self.n_rows, 1, self.dim), None,

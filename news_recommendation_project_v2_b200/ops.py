@@ -283,3 +283,18 @@ def push_rows(src: torch.Tensor, dst_ptrs: list, dst_dtype: torch.dtype, dst_row
     arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
     check(load().nrb_push_rows(ptr(src), dtype_code(src.dtype), src.stride(0), n_rows, dim, arr, len(dst_ptrs),
                                dtype_code(dst_dtype), dst_row_offset, dst_stride, stream_ptr()), "nrb_push_rows")
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Row-wise LayerNorm (nrb_layer_norm): x [rows, dim] fp32/bf16, gamma/beta fp32."""
+    dev = require_device(x.device)
+    _dev(x, "x")
+    _dev(gamma, "gamma", torch.float32)
+    _dev(beta, "beta", torch.float32)
+    rows, dim = x.shape
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(rows, dim, dtype=out_dtype, device=dev)
+    check(load().nrb_layer_norm(ptr(x), dtype_code(x.dtype), x.stride(0), ptr(gamma), ptr(beta), float(eps), ptr(y),
+                                dtype_code(out_dtype), y.stride(0), rows, dim, stream_ptr()), "nrb_layer_norm")
+    return y

@@ -78,6 +78,30 @@ def golden_final(ref, name, dim, hidden, n_rows, n_imp, cand, seed):
     print(name, "scores", out["scores"].shape, "mean metrics", metrics.mean(axis=0))
 
 
+def golden_new_attention(ref):
+    """NewAttention (attention.py:209-279) forward on a padded batch; weights = the reference's own seeded init
+    (LayerNorm affine perturbed so it is exercised), stored because the key set is large and mostly dead."""
+    import news_rec_utils.attention as att
+    dim = 256
+    torch.manual_seed(77)
+    model = att.NewAttention(hidden_size=dim, num_hidden_layers=1).eval()
+    with torch.no_grad():
+        ln = model.encoder.layer[0].g_mlp_layernorm
+        ln.weight.add_(0.1 * torch.randn(dim))
+        ln.bias.add_(0.1 * torch.randn(dim))
+    table = syn.make_table(300, dim, seed=78)
+    imp = syn.make_impressions(21, 300, h_max=12, seed=79)
+    emb, msk = ref.data_utils.final_attention_eval_collate_fn(list(ref.data_utils.group_items(imp.hist_idx, imp.hist_len)), table)
+    with torch.no_grad():
+        out = model(emb, msk)
+    live = {k: v.numpy() for k, v in model.state_dict().items() if "g_mlp_layernorm" in k or k.startswith("linear1")}
+    np.savez_compressed(os.path.join(GOLD, "new_attention_d256.npz"), dim=dim, out=out.numpy(),
+                        keys=np.array(sorted(model.state_dict().keys())),
+                        shapes=np.array([str(tuple(model.state_dict()[k].shape)) for k in sorted(model.state_dict().keys())]),
+                        **{"w::" + k: v for k, v in live.items()})
+    print("new_attention", out.shape)
+
+
 def golden_small(ref):
     du = ref.data_utils
     # collate (data_utils.py:784-791)
@@ -115,6 +139,7 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_harness.load_reference(batch_size=16)
     golden_small(ref)
+    golden_new_attention(ref)
     golden_latent(ref, "latent_cfg1_d768_L512", 768, 512, 32, 64, seed=1234)
     golden_latent(ref, "latent_default_d1024_L64", 1024, 64, 4, 16, seed=4321)
     golden_final(ref, "final_small_d768", 768, 4096, 4096, 64, "small", seed=1234)

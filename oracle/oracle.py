@@ -179,6 +179,22 @@ def final_attention(sd: dict, emb: torch.Tensor, mask: torch.Tensor, dtype=torch
     return (x * w).sum(dim=1)
 
 
+def new_attention(sd: dict, emb: torch.Tensor, mask: torch.Tensor, num_layers: int = 1, dtype=torch.float64) -> torch.Tensor:
+    """NewAttention.forward (attention.py:251-272) as it actually computes: every MyLayer returns
+    g_mlp_layernorm(hidden_states) (attention.py:193, LayerNorm eps 1e-12; the attention / gated-MLP results
+    are discarded), then per-dimension exp weights from linear1, masked normalise (+1e-10), weighted sum."""
+    g = lambda k: sd[k].detach().to(dtype)
+    x = emb.to(dtype)
+    for i in range(num_layers):
+        w, b = g(f"encoder.layer.{i}.g_mlp_layernorm.weight"), g(f"encoder.layer.{i}.g_mlp_layernorm.bias")
+        mu = x.mean(dim=-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+        x = (x - mu) / torch.sqrt(var + 1e-12) * w + b
+    wts = torch.exp(x @ g("linear1.weight").T + g("linear1.bias")) * mask.to(dtype).unsqueeze(-1)
+    wts = wts / (wts.sum(dim=1, keepdim=True) + 1e-10)
+    return (x * wts).sum(dim=1)
+
+
 def user_vectors(sd: dict, table: torch.Tensor, hist_idx: np.ndarray, hist_len: np.ndarray,
                  batch: int = 64, dtype=torch.float64) -> torch.Tensor:
     """get_final_attention_eval (data_model_helper.py:112-131): batches of padded

@@ -225,3 +225,23 @@ def test_mind_metrics_kernel_matches_reference_golden(golden_dir):
     assert np.isnan(per[3]).all() and int(sums[4].item()) == 3
     with pytest.raises(ValueError):
         score(ranks_l, labels_l)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_new_attention_arm(golden_dir, precision, tol):
+    """NewAttention (attention.py:209-279): LayerNorm chain + per-dimension exp pooling, module and engine."""
+    from tests.test_oracle_golden import _new_attention_fixture
+    from news_recommendation_project_v2_b200.attention import NewAttention
+    from news_recommendation_project_v2_b200.data_model_helper import get_cos_sim_scores
+    g, sd, emb, msk, table, imp = _new_attention_fixture(golden_dir)
+    m = NewAttention(hidden_size=int(g["dim"]), num_hidden_layers=1, precision=precision).eval()
+    assert sorted(m.state_dict().keys()) == list(g["keys"])  # dead attention / MLP weights kept for checkpoints
+    assert [str(tuple(m.state_dict()[k].shape)) for k in sorted(m.state_dict())] == list(g["shapes"])
+    m.load_state_dict(sd, strict=False)
+    out = m(emb.cuda(), msk.cuda()).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], atol=tol, rtol=tol)
+    # engine path: per-row tables + fused score/rank
+    sc = get_cos_sim_scores(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, m, precision=precision)
+    u = oracle.new_attention(sd, emb, msk)
+    want = oracle.cosine_scores(u, table, imp.cand_idx, imp.cand_len).numpy()
+    np.testing.assert_allclose(sc.numpy(), want, atol=1e-5 if precision == "fp32" else 5e-3, rtol=0)

@@ -129,3 +129,19 @@ def test_oracle_against_live_reference_if_present():
         want = model(x, mask)
     got = oracle.latent_pool(sd, x, mask, dtype=torch.float32)
     torch.testing.assert_close(got, want, atol=2e-6, rtol=0)
+
+
+def _new_attention_fixture(golden_dir):
+    g = _load(golden_dir, "new_attention_d256")
+    dim = int(g["dim"])
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w::")}
+    table = syn.make_table(300, dim, seed=78)
+    imp = syn.make_impressions(21, 300, h_max=12, seed=79)
+    emb, msk = oracle.final_attention_eval_collate(oracle.group_items(imp.hist_idx, imp.hist_len), table)
+    return g, sd, emb, msk, table, imp
+
+
+def test_new_attention_matches_reference(golden_dir):
+    g, sd, emb, msk, _, _ = _new_attention_fixture(golden_dir)
+    out = oracle.new_attention(sd, emb, msk, num_layers=1, dtype=torch.float64).float().numpy()
+    np.testing.assert_allclose(out, g["out"], atol=3e-6, rtol=1e-5)
