@@ -196,6 +196,20 @@ int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride, int64_t n_
                   void* const* dst_ptrs_host, int world, int dst_dtype, int64_t dst_row_offset,
                   int64_t dst_stride, nrb_stream_t stream);
 
+/* ---- behaviour log -> CSR index builder (host; the step in front of the hot path) ------------------
+ * replaces data_utils.py:168-232 split_impressions_and_history.  `impressions` / `history` are
+ * '\n'-separated UTF-8 buffers with one line per behaviour row (empty history line = no history).
+ * Row ids are assigned in first-appearance order over history-then-impression tokens.  Returns an
+ * opaque handle (NULL on error); query sizes, export into caller-owned HOST arrays, then free.
+ * sizes[0..4] = {n_news, sum_history, n_history_rows, sum_candidates, label_present}. */
+void* nrb_csr_build(const char* impressions, int64_t imp_bytes, const char* history, int64_t hist_bytes,
+                    int64_t n_rows);
+int nrb_csr_sizes(void* handle, int64_t* sizes);
+int nrb_csr_export(void* handle, int32_t* hist_idx, int32_t* hist_owner, int32_t* hist_len,
+                   int32_t* cand_idx, int32_t* cand_owner, int32_t* cand_len, int8_t* labels);
+int64_t nrb_csr_news_ids(void* handle, char* out, int64_t cap);
+void nrb_csr_free(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

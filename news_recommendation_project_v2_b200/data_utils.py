@@ -86,3 +86,45 @@ def final_attention_eval_collate_fn(input: Sequence[np.ndarray], news_embeddings
     if device is not None or news_embeddings.is_cuda:
         return emb, mask
     return emb.cpu(), mask.cpu()
+
+
+def split_impressions_and_history(impressions: Sequence[str], history: Sequence) -> dict:
+    """Behaviour strings -> table row ids + CSR index arrays (data_utils.py:168-232), built by the native
+    host routine `nrb_csr_build` instead of a per-row Python loop.  Same keys / dtypes as the reference:
+    news_list, impression_rev_ind_array int32[2, sum C], impression_len_list int32[I],
+    history_rev_ind_array int32[2, sum H], history_len_list int32[rows with history], labels object[I]."""
+    import ctypes as C
+
+    assert len(impressions) > 0, "No Impressions given"
+    lib = _lib.load()
+    n = len(impressions)
+    imp_buf = "\n".join(impressions).encode()
+    hist_buf = "\n".join(h if isinstance(h, str) else "" for h in history).encode()
+    handle = lib.nrb_csr_build(imp_buf, len(imp_buf), hist_buf, len(hist_buf), n)
+    if not handle:
+        raise _lib.NrbError("nrb_csr_build failed: " + lib.nrb_last_error().decode(errors="replace"))
+    try:
+        sizes = (C.c_int64 * 5)()
+        _lib.check(lib.nrb_csr_sizes(handle, sizes), "nrb_csr_sizes")
+        n_news, n_h, n_hrows, n_c, has_labels = (int(v) for v in sizes)
+        hist = np.empty((2, n_h), dtype=np.int32)
+        cand = np.empty((2, n_c), dtype=np.int32)
+        hist_len = np.empty(n_hrows, dtype=np.int32)
+        cand_len = np.empty(n, dtype=np.int32)
+        labels_flat = np.empty(n_c if has_labels else 0, dtype=np.int8)
+        p = lambda a: a.ctypes.data if a.size else None
+        _lib.check(lib.nrb_csr_export(handle, p(hist[0]), p(hist[1]), p(hist_len), p(cand[0]), p(cand[1]),
+                                      p(cand_len), p(labels_flat)), "nrb_csr_export")
+        need = lib.nrb_csr_news_ids(handle, None, 0)
+        buf = C.create_string_buffer(int(need) + 1)
+        lib.nrb_csr_news_ids(handle, buf, need)
+        news_list = np.array(buf.raw[:need].decode().split("\n")[:-1])
+    finally:
+        lib.nrb_csr_free(handle)
+    labels = np.empty(n if has_labels else 0, dtype=object)
+    if has_labels:
+        off = csr_offsets(cand_len)
+        for i in range(n):
+            labels[i] = tuple(int(v) for v in labels_flat[off[i]:off[i + 1]])
+    return {"news_list": news_list, "impression_rev_ind_array": cand, "impression_len_list": cand_len,
+            "history_rev_ind_array": hist, "history_len_list": hist_len, "labels": labels}

@@ -155,3 +155,32 @@ def test_table_shard_bounds():
     assert b == [(0, 20_002), (20_002, 40_003)]
     b = table_shard_bounds(5, 8)  # more ranks than rows: trailing shards are empty
     assert b[:5] == [(i, i + 1) for i in range(5)] and all(x == (5, 5) for x in b[5:])
+
+
+def test_native_csr_builder_matches_reference(golden_dir):
+    """nrb_csr_build (host C++) vs the reference's split_impressions_and_history golden + a random log."""
+    from news_recommendation_project_v2_b200.data_utils import split_impressions_and_history
+    from oracle import oracle
+    g = np.load(os.path.join(golden_dir, "small_cases.npz"))
+    impressions = ["N1-0 N2-1 N3-0", "N2-0 N4-1", "N5-1 N1-0 N6-0 N7-0"]
+    history = ["N9 N1 N8", "N8", "N4 N9 N10 N2"]
+    sp = split_impressions_and_history(impressions, history)
+    assert list(sp["news_list"]) == list(g["split_news"])
+    for a, b in (("impression_rev_ind_array", "split_imp"), ("impression_len_list", "split_imp_len"),
+                 ("history_rev_ind_array", "split_hist"), ("history_len_list", "split_hist_len")):
+        assert np.array_equal(sp[a], g[b]) and sp[a].dtype == np.int32
+    assert [list(l) for l in sp["labels"]] == [[0, 1, 0], [0, 1], [1, 0, 0, 0]]
+    # random log with missing histories (None / ""), no labels, repeated ids -- against the oracle restatement
+    rng = np.random.default_rng(3)
+    ids = [f"N{rng.integers(0, 400)}" for _ in range(6000)]
+    imps, hists, k = [], [], 0
+    for r in range(500):
+        c, h = int(rng.integers(1, 9)), int(rng.integers(0, 6))
+        imps.append(" ".join(ids[k:k + c]))
+        hists.append(None if h == 0 and r % 2 else " ".join(ids[k + c:k + c + h]))
+        k += c + h
+    want = oracle.split_impressions_and_history(imps, [h if h else "" for h in hists])
+    got = split_impressions_and_history(imps, hists)
+    assert list(got["news_list"]) == list(want["news_list"]) and len(got["labels"]) == 0
+    for key in ("impression_rev_ind_array", "impression_len_list", "history_rev_ind_array", "history_len_list"):
+        assert np.array_equal(got[key], want[key])
