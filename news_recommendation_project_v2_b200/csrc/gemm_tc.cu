@@ -27,6 +27,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace nrb {
@@ -41,13 +42,14 @@ constexpr int kGroupBytes = kBM * 128;  // one 128-row x 64-column bf16 staging 
 constexpr int kMaxCluster = 8;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN, int EPI, bool OUT_BF16>
+template <int BN, int EPI, bool OUT_BF16, int CG = 1>
 struct GemmCfg {
+  static_assert(CG == 1 || (CG == 2 && BN == 256 && EPI != NRB_EPI_SOFTMAX), "CTA pairs: 256-wide tiles, no softmax");
   static constexpr bool kStaged = OUT_BF16;
   static constexpr bool kSoftmax = EPI == NRB_EPI_SOFTMAX;
   static constexpr int kHalves = BN / 128;  // epilogue column halves (128 accumulator columns each)
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;  // a CTA pair splits the N rows of W between its two CTAs
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kStaged ? kHalves * kGroupBytes : 0;
   static constexpr int kXchgBytes = kSoftmax ? 2 * 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [parity][m|s][participant][row]
@@ -162,11 +164,11 @@ __device__ __forceinline__ void stage_values(uint32_t base, int r, int j0, const
                  pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
 }
 
-template <int BN, int EPI, bool OUT_BF16>
+template <int BN, int EPI, bool OUT_BF16, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
-  using Cfg = GemmCfg<BN, EPI, OUT_BF16>;
+  using Cfg = GemmCfg<BN, EPI, OUT_BF16, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kHalves = Cfg::kHalves;
   constexpr bool kGeglu = EPI == NRB_EPI_GEGLU;
@@ -187,13 +189,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CS: CTAs of a cluster share one 128-row block and take neighbouring N tiles (softmax statistics exchange)
+  // CG: CTA pair (cta_group::2): two neighbouring 128-row blocks, ONE N tile; tcgen05.mma spans both SMs
   const int CS = Cfg::kSoftmax ? p.cluster : 1;
-  const uint32_t cta_rank = CS > 1 ? ptx::cluster_ctarank() : 0;
-  const uint32_t unit = CS > 1 ? ptx::cluster_id_x() : blockIdx.x;  // scheduling unit = cluster
-  const uint32_t n_units = CS > 1 ? ptx::num_clusters_x() : gridDim.x;
+  const bool clustered = CS > 1 || CG == 2;
+  const uint32_t cta_rank = clustered ? ptx::cluster_ctarank() : 0;
+  const uint32_t unit = clustered ? ptx::cluster_id_x() : blockIdx.x;  // scheduling unit = cluster
+  const uint32_t n_units = clustered ? ptx::num_clusters_x() : gridDim.x;
 
   const int64_t M = p.m_dev != nullptr ? min(p.M, (int64_t)*p.m_dev) : p.M;
-  const int m_tiles = (int)((M + kBM - 1) / kBM);
+  const int m_tiles = (int)((M + kBM * CG - 1) / (kBM * CG));  // row blocks per scheduling unit: 128*CG rows
   const int n_tiles = (p.N + BN - 1) / BN;
   const int n_units_per_row = n_tiles / CS;  // host guarantees n_tiles % CS == 0
   const int64_t total_units = (int64_t)m_tiles * n_units_per_row;
@@ -206,23 +211,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], 1);  // pair: only the leader arrives (expect_tx covers both CTAs' bytes)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4 * kHalves);   // one arrive per active epilogue warp
+      ptx::mbar_init(&tmem_empty[s], 4 * kHalves * CG);  // one arrive per active epilogue warp (of both CTAs)
       ptx::mbar_init(&xbar[s], 4 * kHalves * CS);    // one arrive per epilogue warp of every CTA in the cluster
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CS > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
+  if (clustered) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -232,10 +242,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t u = unit; u < total_units; u += n_units) {
-        const int m_blk = (int)(u / n_units_per_row);
-        const int n_blk = (int)(u % n_units_per_row) * CS + (int)cta_rank;
+        const int m_blk = (int)(u / n_units_per_row) * CG + (CG == 2 ? (int)cta_rank : 0);
+        const int n_blk = (int)(u % n_units_per_row) * CS + (CG == 2 ? 0 : (int)cta_rank);
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (CG == 2) {
+            // both CTAs fill their own smem; all bytes are counted on the LEADER's barrier
+            const uint32_t lbar = ptx::leader_addr(ptx::smem_u32(&full_bar[stage]));
+            // (the peer's bytes can only be issued after the stage's previous phase completed, so they are
+            //  always accounted to the right phase even if they land before the leader's expect_tx)
+            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            ptx::tma_load_2d_cg2(smem_a + stage * Cfg::kABytes, &map_a, lbar, kb * kBK, m_blk * kBM);
+            ptx::tma_load_2d_cg2(smem_b + stage * Cfg::kBBytes, &map_w, lbar, kb * kBK,
+                                 n_blk * BN + (int)cta_rank * (BN / 2));
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], kb * kBK, m_blk * kBM);
           ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_w, &full_bar[stage], kb * kBK, n_blk * BN);
@@ -248,8 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+    if (lane == 0 && (CG == 1 || cta_rank == 0)) {  // pair: only the leader CTA issues
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -267,15 +292,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * kUmmaK * 2);
             const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 2);
-            ptx::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              ptx::mma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              ptx::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          // smem stage reusable once these MMAs retire (pair: signalled in both CTAs)
+          if (CG == 2)
+            ptx::mma_commit_cg2(&empty_bar[stage]);
+          else
+            ptx::mma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::mma_commit(&tmem_full[acc]);  // accumulator complete
+        if (CG == 2)
+          ptx::mma_commit_cg2(&tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
+        else
+          ptx::mma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -294,9 +329,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;
+    // accumulator hand-back: the (leader's) MMA warp waits for every epilogue warp of the pair
+    auto release_tmem = [&](int a) {
+      if (CG == 2)
+        ptx::mbar_arrive_cluster(ptx::leader_addr(ptx::smem_u32(&tmem_empty[a])));
+      else
+        ptx::mbar_arrive(&tmem_empty[a]);
+    };
     for (int64_t u = unit; u < total_units; u += n_units, ++it) {
-      const int m_blk = (int)(u / n_units_per_row);
-      const int n_blk = (int)(u % n_units_per_row) * CS + (int)cta_rank;
+      const int m_blk = (int)(u / n_units_per_row) * CG + (CG == 2 ? (int)cta_rank : 0);
+      const int n_blk = (int)(u % n_units_per_row) * CS + (CG == 2 ? 0 : (int)cta_rank);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t row = (int64_t)m_blk * kBM + r_tile;
@@ -395,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (c == 3) {  // accumulator fully consumed: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) release_tmem(acc);
           }
           const float shift = fmaf(mx[c], kLog2e, __log2f(sm[c]));  // M*log2e + log2 S
           float v[32];
@@ -432,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (c == 3) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) release_tmem(acc);
           }
           float v[32];
           if (active) activate_chunk<EPI>(r, p, row, col0, row_ok, v);
@@ -486,7 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) release_tmem(acc);
       }
       if (++acc == 2) {
         acc = 0;
@@ -498,10 +540,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CS > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still write its shared memory
+  if (clustered) ptx::cluster_sync_all();  // no CTA may exit while a peer can still touch its smem / TMEM
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2)
+      ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else
+      ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -548,18 +593,19 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols
   return NRB_OK;
 }
 
-template <int BN, int EPI, bool OUT_BF16>
+template <int BN, int EPI, bool OUT_BF16, int CG = 1>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my, const GemmParams& p,
                        cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EPI, OUT_BF16>;
-  auto kern = gemm_tc_kernel<BN, EPI, OUT_BF16>;
+  using Cfg = GemmCfg<BN, EPI, OUT_BF16, CG>;
+  auto kern = gemm_tc_kernel<BN, EPI, OUT_BF16, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     NRB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int cs = Cfg::kSoftmax ? p.cluster : 1;
-  const int64_t units = ((p.M + kBM - 1) / kBM) * (int64_t)(((p.N + BN - 1) / BN) / cs);
+  const int cs = CG == 2 ? 2 : (Cfg::kSoftmax ? p.cluster : 1);
+  const int n_split = CG == 2 ? 1 : cs;
+  const int64_t units = ((p.M + kBM * CG - 1) / (kBM * CG)) * (int64_t)(((p.N + BN - 1) / BN) / n_split);
   const int max_units = sm_count_cached() / cs;
   const int grid = (int)std::min<int64_t>(units, max_units) * cs;
   if (cs > 1) {
@@ -584,20 +630,20 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   return NRB_OK;
 }
 
-template <int BN, bool OUT_BF16>
+template <int BN, bool OUT_BF16, int CG = 1>
 static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my,
                         const GemmParams& p, cudaStream_t st) {
   switch (epi) {
     case NRB_EPI_NONE:
-      return launch_gemm<BN, NRB_EPI_NONE, OUT_BF16>(ma, mw, my, p, st);
+      return launch_gemm<BN, NRB_EPI_NONE, OUT_BF16, CG>(ma, mw, my, p, st);
     case NRB_EPI_RELU:
-      return launch_gemm<BN, NRB_EPI_RELU, OUT_BF16>(ma, mw, my, p, st);
+      return launch_gemm<BN, NRB_EPI_RELU, OUT_BF16, CG>(ma, mw, my, p, st);
     case NRB_EPI_EXP:
-      return launch_gemm<BN, NRB_EPI_EXP, OUT_BF16>(ma, mw, my, p, st);
+      return launch_gemm<BN, NRB_EPI_EXP, OUT_BF16, CG>(ma, mw, my, p, st);
     case NRB_EPI_RESIDUAL:
-      return launch_gemm<BN, NRB_EPI_RESIDUAL, OUT_BF16>(ma, mw, my, p, st);
+      return launch_gemm<BN, NRB_EPI_RESIDUAL, OUT_BF16, CG>(ma, mw, my, p, st);
     case NRB_EPI_GEGLU:
-      return launch_gemm<BN, NRB_EPI_GEGLU, OUT_BF16>(ma, mw, my, p, st);
+      return launch_gemm<BN, NRB_EPI_GEGLU, OUT_BF16, CG>(ma, mw, my, p, st);
     default:
       set_error("nrb_linear(bf16): unsupported epilogue %d", epi);
       return NRB_E_INVALID;
@@ -631,10 +677,17 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
     cluster = group > 256 ? group / 256 : 1;
   }
   const bool small_n = N <= 128 && !softmax;
+  // CTA pairs (tcgen05 cta_group::2): each SM stages only half of the W tile -> 1/3 less shared-memory
+  // operand traffic per MMA.  NRB200_GEMM_2CTA=0 selects the single-CTA kernel.
+  static const bool pair_enabled = [] {
+    const char* e = getenv("NRB200_GEMM_2CTA");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool pair = pair_enabled && !small_n && !softmax && M > kBM;
   CUtensorMap ma, mw, my;
   int rc = make_tmap_bf16(&ma, a, M, K, lda, kBM);
   if (rc != NRB_OK) return rc;
-  rc = make_tmap_bf16(&mw, w, N, K, ldw, small_n ? 128 : 256);
+  rc = make_tmap_bf16(&mw, w, N, K, ldw, (small_n || pair) ? 128 : 256);
   if (rc != NRB_OK) return rc;
   const int n_out = epi == NRB_EPI_GEGLU ? N / 2 : N;
   if (out_dtype == NRB_BF16) {
@@ -660,6 +713,10 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   if (small_n) {
     return out_dtype == NRB_BF16 ? dispatch_epi<128, true>(epi, ma, mw, my, p, st)
                                  : dispatch_epi<128, false>(epi, ma, mw, my, p, st);
+  }
+  if (pair) {
+    return out_dtype == NRB_BF16 ? dispatch_epi<256, true, 2>(epi, ma, mw, my, p, st)
+                                 : dispatch_epi<256, false, 2>(epi, ma, mw, my, p, st);
   }
   return out_dtype == NRB_BF16 ? dispatch_epi<256, true>(epi, ma, mw, my, p, st)
                                : dispatch_epi<256, false>(epi, ma, mw, my, p, st);
