@@ -107,7 +107,7 @@ int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
  *   precision NRB_F32 : a, w are fp32, FFMA accumulation (the reference's own fp32 arithmetic).
  * out_dtype selects the dtype of y (and of `res` for NRB_EPI_RESIDUAL, which is fp32).
  * For GEGLU y has N/2 columns.  SOFTMAX (bf16 precision, bf16 output only): every `group` consecutive
- * columns (a power of two in [32, 2048], N % 256 == 0) form one softmax row of which the first
+ * columns (a power of two in [32, 1024], N % 256 == 0) form one softmax row of which the first
  * `group_valid` are real; groups wider than one 256-column tile are computed by a thread-block cluster
  * that exchanges the row statistics through distributed shared memory. */
 int nrb_linear(int precision, int epilogue, int out_dtype,

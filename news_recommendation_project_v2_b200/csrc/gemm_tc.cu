@@ -39,7 +39,7 @@ constexpr int kCtrlWarps = 4;  // TMA, MMA, TMEM-alloc, spare
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = (kCtrlWarps + kEpiWarps) * 32;
 constexpr int kGroupBytes = kBM * 128;  // one 128-row x 64-column bf16 staging group (swizzle-128B)
-constexpr int kMaxCluster = 8;
+constexpr int kMaxCluster = 4;  // softmax groups up to 4 x 256 = 1024 columns
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in limit per CTA
 
 template <int BN, int EPI, bool OUT_BF16, int CG = 1>
@@ -51,7 +51,7 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;  // a CTA pair splits the N rows of W between its two CTAs
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kStaged ? kHalves * kGroupBytes : 0;
+  static constexpr int kStagingBytes = kStaged ? kHalves * 2 * kGroupBytes : 0;  // double buffered per half
   static constexpr int kXchgBytes = kSoftmax ? 2 * 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [parity][m|s][participant][row]
   static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXchgBytes;
   static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
@@ -177,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // [kHalves][16 KB], 1024-aligned
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // [kHalves][2][16 KB], 1024-aligned
   float* xbuf = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][2*kMaxCluster][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kXchgBytes);
   uint64_t* full_bar = bars;                      // [kStages] TMA -> MMA
@@ -325,7 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int r_tile = quad * 32 + lane;
     const bool issuer = (quad == 0 && lane == 0);
     const int bar_id = 1 + hf;  // named barrier of this half (128 threads)
-    const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(hf * kGroupBytes);
+    uint8_t* const stg_base = staging + hf * 2 * kGroupBytes;  // this half's two staging buffers
+    uint32_t gsel = 0;                                           // which of the two the next group uses
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;
@@ -351,11 +352,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // pass A: per 32-column chunk (m_c, s_c = sum exp(x - m_c)); chunks merged to the group in registers;
         //         groups wider than this warp's 128 columns merge the (m, s) pairs of all participants
         //         (the other half of this CTA and the other CTAs of the cluster) through DSMEM.
-        // pass B: p = 2^(x*log2e - (M*log2e + log2 S)): normalised in the exponent, one bf16 rounding.
+        //         exp(x - m_c) is written back to TMEM in place of the logit (tcgen05.st).
+        // pass B: p = TMEM value * 2^((m_c - M) log2e) / S: one ex2 per element, one bf16 rounding.
         const int lp = p.group, lv = p.group_valid;
         const bool masked = lv < lp;
         const bool half_ok = colh < p.N;
-        float mx[4], sm[4];
+        float mx[4], sm[4], mcb[4];  // group max / sum, chunk-local max * log2e
         uint32_t rbuf[2][32];
         ptx::tmem_ld_32x32(taddr, rbuf[0]);
 #pragma unroll
@@ -375,11 +377,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           const float mb = (m == -INFINITY ? 0.f : m) * kLog2e;  // an all-masked chunk contributes nothing
           float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ev[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_approx(fmaf(xv[j], kLog2e, -mb));
+          for (int j = 0; j < 32; ++j) {
+            const float e = ex2_approx(fmaf(xv[j], kLog2e, -mb));
+            s4[j & 3] += e;
+            ev[j] = __float_as_uint(e);
+          }
+          // exp(x - m_c) replaces the logit IN TMEM: pass B only rescales, so each element costs one ex2
+          ptx::tmem_st_32x32(taddr + (uint32_t)(c * 32), ev);
           mx[c] = m;
+          mcb[c] = mb;
           sm[c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         }
+        ptx::tmem_st_wait();
         // merge (m, s) pairs: s_total = sum_c s_c * 2^((m_c - m) log2e)
         auto merge2 = [](float& ma, float& sa, float mb_, float sb_) {
           const float m = fmaxf(ma, mb_);
@@ -439,25 +450,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) release_tmem(acc);
           }
-          const float shift = fmaf(mx[c], kLog2e, __log2f(sm[c]));  // M*log2e + log2 S
+          // p = exp(x - m_c) * 2^((m_c - M) log2e) / S   (masked columns already hold exp(-inf) = 0)
+          const float f = ex2_approx(mcb[c] - mx[c] * kLog2e) / sm[c];
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = !masked || (((colh + c * 32 + j) & (lp - 1)) < lv);
-            v[j] = ok ? ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -shift)) : 0.f;
-          }
-          if ((c & 1) == 0) {  // first chunk of a group: the staging buffer must be free again
-            if (issuer) ptx::tma_store_wait_read();
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * f;
+          if ((c & 1) == 0) {  // first chunk of a group: the buffer used two groups ago must be drained
+            if (issuer) ptx::tma_store_wait_read1();
             ptx::named_bar_sync(bar_id, 128);
           }
-          stage_values<32>(stg, r_tile, (c & 1) * 4, v);
+          stage_values<32>(ptx::smem_u32(stg_base + gsel * kGroupBytes), r_tile, (c & 1) * 4, v);
           if ((c & 1) == 1) {
             ptx::fence_proxy_async();
             ptx::named_bar_sync(bar_id, 128);
-            if (issuer && half_ok) {
-              ptx::tma_store_2d(&map_y, staging + hf * kGroupBytes, colh + (c >> 1) * 64, m_blk * kBM);
-              ptx::tma_store_commit();
+            if (issuer) {
+              if (half_ok) ptx::tma_store_2d(&map_y, stg_base + gsel * kGroupBytes, colh + (c >> 1) * 64, m_blk * kBM);
+              ptx::tma_store_commit();  // committed even when empty: keeps the group count in step with gsel
             }
+            gsel ^= 1;
           }
         }
       } else if constexpr (Cfg::kStaged) {
@@ -481,9 +491,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           constexpr int kChunksPerGroup = kGeglu ? 4 : 2;  // accumulator chunks that fill one 64-column group
           const int cg = c % kChunksPerGroup;
           if (cg == 0) {
-            if (issuer) ptx::tma_store_wait_read();
+            if (issuer) ptx::tma_store_wait_read1();
             ptx::named_bar_sync(bar_id, 128);
           }
+          const uint32_t stg = ptx::smem_u32(stg_base + gsel * kGroupBytes);
           if (active) {
             if (kGeglu)
               stage_values<16>(stg, r_tile, cg * 2, v);
@@ -495,10 +506,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::named_bar_sync(bar_id, 128);
             const int out_col = kGeglu ? (colh >> 1) : (colh + (c / 2) * 64);
             const int n_out = kGeglu ? (p.N >> 1) : p.N;
-            if (issuer && out_col < n_out) {
-              ptx::tma_store_2d(&map_y, staging + hf * kGroupBytes, out_col, m_blk * kBM);
-              ptx::tma_store_commit();
+            if (issuer) {
+              if (out_col < n_out) ptx::tma_store_2d(&map_y, stg_base + gsel * kGroupBytes, out_col, m_blk * kBM);
+              ptx::tma_store_commit();  // committed even when empty: keeps the group count in step with gsel
             }
+            gsel ^= 1;
           }
         }
       } else {

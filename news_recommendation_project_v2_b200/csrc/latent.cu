@@ -313,7 +313,7 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
                               st)) != NRB_OK)
       return rc;
     // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
-    if (P == NRB_BF16 && hl % 256 == 0) {
+    if (P == NRB_BF16 && hl % 256 == 0 && w->latents_padded <= 1024) {
       // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
       if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
                        st, w->latents_padded, w->num_latents)) != NRB_OK)

@@ -96,7 +96,6 @@ def test_final_attention_rows_vs_oracle(ops, precision, tol):
     (300, 512, 128, 256, 256), (300, 768, 128, 256, 130),          # group == one 256-column tile
     (700, 1024, 256, 512, 512), (129, 4096, 768, 512, 512),        # cluster of 2 (BASELINE L=512)
     (520, 2048, 128, 1024, 1000),                                  # cluster of 4 (BASELINE cfg 5, L=1024)
-    (200, 2048, 64, 2048, 2048),                                   # cluster of 8
 ])
 def test_linear_softmax_epilogue_cluster(ops, M, N, K, group, valid):
     """Per-group softmax fused behind the contraction; groups wider than a tile span a CTA cluster (DSMEM)."""
