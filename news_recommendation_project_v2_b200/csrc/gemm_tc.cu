@@ -217,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 4 * kHalves * CG);  // one arrive per active epilogue warp (of both CTAs)
-      ptx::mbar_init(&xbar[s], 4 * kHalves * CS);    // one arrive per epilogue warp of every CTA in the cluster
+      ptx::mbar_init(&xbar[s], 1);  // one local expect_tx arrive per tile; the statistics arrive as st.async bytes
     }
     ptx::fence_barrier_init();
   }
@@ -332,8 +332,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t it = 0;
     // accumulator hand-back: the (leader's) MMA warp waits for every epilogue warp of the pair
     auto release_tmem = [&](int a) {
-      if (CG == 2)
-        ptx::mbar_arrive_cluster(ptx::leader_addr(ptx::smem_u32(&tmem_empty[a])));
+      // (TMEM reads are ordered by tcgen05.fence::before_thread_sync; no memory release is needed, which
+      //  spares the peer CTA a cluster-scope MEMBAR per tile)
+      if (CG == 2 && cta_rank != 0)
+        ptx::mbar_arrive_cluster_relaxed(ptx::leader_addr(ptx::smem_u32(&tmem_empty[a])));
       else
         ptx::mbar_arrive(&tmem_empty[a]);
     };
@@ -415,27 +417,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int n_part = kHalves * CS;
           const uint32_t parity = it & 1;
           const int me = (int)cta_rank * kHalves + hf;
-          // slots are double buffered by tile parity: a peer can reuse buffer `parity` only two tiles later,
-          // which requires this thread's arrival at the next exchange, i.e. after it has read these slots
-          float* xb = xbuf + parity * (2 * 2 * kMaxCluster * 128);
-          const uint32_t slot_m = ptx::smem_u32(xb + (0 * 2 * kMaxCluster + me) * 128 + r_tile);
-          const uint32_t slot_s = ptx::smem_u32(xb + (1 * 2 * kMaxCluster + me) * 128 + r_tile);
-          for (int c = 0; c < CS; ++c) {
-            ptx::st_cluster_f32(ptx::map_to_cta(slot_m, c), mx[0]);
-            ptx::st_cluster_f32(ptx::map_to_cta(slot_s, c), sm[0]);
-          }
-          // one release-arrive per warp and destination: the lanes' stores are ordered before it by
-          // __syncwarp (cta scope) and made visible cluster-wide by the cumulative release
-          __syncwarp();
-          if (lane == 0)
-            for (int c = 0; c < CS; ++c) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&xbar[0]), c));
-          ptx::mbar_wait_cluster(&xbar[0], parity);
+          // (m, s) pairs travel as st.async (DSMEM) whose completion bytes are counted on the DESTINATION's
+          // mbarrier: no release fence on the producer side.  Slots and barriers alternate with the tile
+          // parity: a peer can reach tile it+2 (same parity) only after this thread contributed to it+1,
+          // i.e. after it has read the slots of tile `it`.
+          float2* xb2 = reinterpret_cast<float2*>(xbuf) + parity * (2 * kMaxCluster * 128);
+          if (e == 0 && lane == 0) ptx::mbar_expect_tx(&xbar[parity], (uint32_t)(n_part * 128 * 8));
+          const uint32_t slot = ptx::smem_u32(xb2 + me * 128 + r_tile);
+          const uint32_t bar = ptx::smem_u32(&xbar[parity]);
+          for (int c = 0; c < CS; ++c)
+            ptx::st_async_v2_f32(ptx::map_to_cta(slot, c), mx[0], sm[0], ptx::map_to_cta(bar, c));
+          ptx::mbar_wait(&xbar[parity], (it >> 1) & 1);
           float m = -INFINITY;
-          for (int q = 0; q < n_part; ++q) m = fmaxf(m, xb[(0 * 2 * kMaxCluster + q) * 128 + r_tile]);
+          for (int q = 0; q < n_part; ++q) m = fmaxf(m, xb2[q * 128 + r_tile].x);
           float st = 0.f;
-          for (int q = 0; q < n_part; ++q)
-            st += xb[(1 * 2 * kMaxCluster + q) * 128 + r_tile] *
-                  ex2_approx((xb[(0 * 2 * kMaxCluster + q) * 128 + r_tile] - m) * kLog2e);
+          for (int q = 0; q < n_part; ++q) {
+            const float2 ms = xb2[q * 128 + r_tile];
+            st += ms.y * ex2_approx((ms.x - m) * kLog2e);
+          }
           mx[0] = mx[1] = mx[2] = mx[3] = m;
           sm[0] = sm[1] = sm[2] = sm[3] = st;
         }
@@ -620,7 +619,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   const int64_t units = ((p.M + kBM * CG - 1) / (kBM * CG)) * (int64_t)(((p.N + BN - 1) / BN) / n_split);
   const int max_units = sm_count_cached() / cs;
   const int grid = (int)std::min<int64_t>(units, max_units) * cs;
-  if (cs > 1) {
+  if (cs > 1 || Cfg::kSoftmax) {  // softmax always launches as a cluster (st.async / mapa need one, even of size 1)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);

@@ -219,8 +219,20 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
+// asynchronous DSMEM store of two floats; completion is counted (8 bytes) on the DESTINATION CTA's mbarrier,
+// so the producer needs no release fence and the consumer's mbarrier wait makes the data visible
+__device__ __forceinline__ void st_async_v2_f32(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                   cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_bar_addr)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+// remote arrive WITHOUT a memory release: enough when the ordering that matters is carried by tcgen05 fences
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
