@@ -318,7 +318,7 @@ def bench_stage_a(dev, peaks, args):
             out = m(x, mask)
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
+        reps = 5
         t0.record()
         for _ in range(reps):
             out = m(x, mask)
