@@ -12,7 +12,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnrb200.so")
+LIB_PATH = os.environ.get("NRB200_LIB") or os.path.join(_PKG, "libnrb200.so")  # NRB200_LIB: A/B experiments only
 
 F32, BF16 = 0, 1
 POOL_FINAL_ATTENTION, POOL_MEAN_L2 = 0, 1
