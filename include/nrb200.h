@@ -177,6 +177,15 @@ int nrb_latent_forward(const nrb_latent_weights* w, const void* x, int x_dtype,
                        void* workspace, size_t workspace_bytes, int64_t max_tokens,
                        int64_t* n_tokens_host, nrb_stream_t stream);
 
+/* Varlen form of nrb_latent_forward: x_packed [n_tokens, dim] holds only real tokens, item_off (device int32
+ * [batch+1]) their CSR offsets per item -- the layout a packed token store produces (the reference pads each
+ * batch to its longest item and masks: data_utils.py:878-933, 753-781).  One chunk: the caller keeps
+ * n_tokens <= the max_tokens the workspace was sized for. */
+int nrb_latent_forward_packed(const nrb_latent_weights* w, const void* x_packed, int x_dtype,
+                              int64_t n_tokens, const int32_t* item_off, int64_t batch,
+                              float* pooled_out, void* workspace, size_t workspace_bytes,
+                              nrb_stream_t stream);
+
 /* ---- MIND metrics on device (consumer of the ranks; "next" row of the hot path) ---------------
  * replaces evaluation.py:34-98 (score_row per impression in a 4-process pool + mean):
  * per impression AUC (tie-aware, = sklearn roc_auc_score), MRR, nDCG@5, nDCG@10 from dense ranks and

@@ -67,6 +67,8 @@ PROTOTYPES = {
     "nrb_csr_export": (_i32, [_c_void_p] * 8),
     "nrb_csr_news_ids": (_i64, [_c_void_p, _c_void_p, _i64]),
     "nrb_csr_free": (None, [_c_void_p]),
+    "nrb_latent_forward_packed": (_i32, [C.POINTER(LatentWeights), _c_void_p, _i32, _i64, _c_void_p, _i64,
+                                         _c_void_p, _c_void_p, _sz, _c_void_p]),
     "nrb_latent_forward": (_i32, [C.POINTER(LatentWeights), _c_void_p, _i32, _i64, _i32, _c_void_p,
                                   _c_void_p, _c_void_p, _c_void_p, _sz, _i64, C.POINTER(_i64), _c_void_p]),
 }

@@ -249,6 +249,50 @@ extern "C" int nrb_latent_fold(int precision, int dim, int heads, int dim_head, 
   return NRB_OK;
 }
 
+// LN -> logits GEMM + per-head softmax -> value GEMM + residual -> LN -> GEGLU GEMM -> output GEMM + residual for
+// `rows_cap` packed token rows (effective count *m_dev when given); h2 receives the fp32 block output.
+static int latent_block_rows(const nrb_latent_weights* w, const FwdWs& f, const void* xc, int x_dtype,
+                             const int32_t* row_map, const int* m_dev, int64_t rows_cap, float* h2, cudaStream_t st) {
+  const int d = w->dim, P = w->precision;
+  const int hl = w->heads * w->latents_padded;
+  int rc;
+    // xn = LN1(x) (packed), xres = x (fp32)                      latent_attention.py:16
+    if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, f.xres, d, rows_cap, m_dev, d,
+                              st)) != NRB_OK)
+      return rc;
+    // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
+    if (P == NRB_BF16 && hl % 256 == 0 && w->latents_padded <= 1024) {
+      // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
+      if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
+                       st, w->latents_padded, w->num_latents)) != NRB_OK)
+        return rc;
+    } else {
+      if ((rc = linear(P, NRB_EPI_NONE, NRB_F32, f.xn, d, w->a, d, nullptr, nullptr, 0, f.logits, hl, rows_cap,
+                       m_dev, hl, d, st)) != NRB_OK)
+        return rc;
+      if ((rc = softmax_groups(f.logits, hl, f.p, P, hl, rows_cap, m_dev, w->heads, w->latents_padded,
+                               w->num_latents, st)) != NRB_OK)
+        return rc;
+    }
+    // h1 = P B^T + x                                               :74, :162
+    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, f.xres, d, f.h1, d, rows_cap, m_dev,
+                     d, hl, st)) != NRB_OK)
+      return rc;
+    // hn = LN2(h1)                                                 :16 (second PreNorm)
+    if ((rc = layer_norm_rows(f.h1, NRB_F32, d, nullptr, w->ln2_w, w->ln2_b, f.hn, P, d, nullptr, 0, rows_cap, m_dev,
+                              d, st)) != NRB_OK)
+      return rc;
+    // g = GEGLU(hn W1^T + b1)                                      :33-35, 24-27
+    if ((rc = linear(P, NRB_EPI_GEGLU, P, f.hn, d, w->w_ff1, d, w->b_ff1, nullptr, 0, f.g, 4 * d, rows_cap, m_dev,
+                     8 * d, d, st)) != NRB_OK)
+      return rc;
+    // h2 = g W2^T + b2 + h1                                        :36, :163
+    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.g, 4 * d, w->w_ff2, 4 * d, w->b_ff2, f.h1, d, h2, d, rows_cap,
+                     m_dev, d, 4 * d, st)) != NRB_OK)
+      return rc;
+  return NRB_OK;
+}
+
 static int64_t chunk_items_for(int64_t max_tokens, int seq) { return std::max<int64_t>(1, max_tokens / seq); }
 
 extern "C" size_t nrb_latent_forward_workspace_bytes(const nrb_latent_weights* w, int64_t max_tokens) {
@@ -286,8 +330,7 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
     return NRB_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  const int d = w->dim, P = w->precision;
-  const int hl = w->heads * w->latents_padded;
+  const int d = w->dim;
   const size_t xs = dtype_size(x_dtype);
   const bool packed = pooled_out != nullptr;
   const int sms = sm_count_cached();
@@ -308,46 +351,40 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
       row_map = f.row_map;
       m_dev = f.m_dev;
     }
-    // xn = LN1(x) (packed), xres = x (fp32)                      latent_attention.py:16
-    if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, f.xres, d, rows_cap, m_dev, d,
-                              st)) != NRB_OK)
-      return rc;
-    // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
-    if (P == NRB_BF16 && hl % 256 == 0 && w->latents_padded <= 1024) {
-      // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
-      if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
-                       st, w->latents_padded, w->num_latents)) != NRB_OK)
-        return rc;
-    } else {
-      if ((rc = linear(P, NRB_EPI_NONE, NRB_F32, f.xn, d, w->a, d, nullptr, nullptr, 0, f.logits, hl, rows_cap,
-                       m_dev, hl, d, st)) != NRB_OK)
-        return rc;
-      if ((rc = softmax_groups(f.logits, hl, f.p, P, hl, rows_cap, m_dev, w->heads, w->latents_padded,
-                               w->num_latents, st)) != NRB_OK)
-        return rc;
-    }
-    // h1 = P B^T + x                                               :74, :162
-    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, f.xres, d, f.h1, d, rows_cap, m_dev,
-                     d, hl, st)) != NRB_OK)
-      return rc;
-    // hn = LN2(h1)                                                 :16 (second PreNorm)
-    if ((rc = layer_norm_rows(f.h1, NRB_F32, d, nullptr, w->ln2_w, w->ln2_b, f.hn, P, d, nullptr, 0, rows_cap, m_dev,
-                              d, st)) != NRB_OK)
-      return rc;
-    // g = GEGLU(hn W1^T + b1)                                      :33-35, 24-27
-    if ((rc = linear(P, NRB_EPI_GEGLU, P, f.hn, d, w->w_ff1, d, w->b_ff1, nullptr, 0, f.g, 4 * d, rows_cap, m_dev,
-                     8 * d, d, st)) != NRB_OK)
-      return rc;
-    // h2 = g W2^T + b2 + h1                                        :36, :163
     float* h2 = packed ? f.h2 : unpooled_out + (size_t)i0 * seq * d;
-    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.g, 4 * d, w->w_ff2, 4 * d, w->b_ff2, f.h1, d, h2, d, rows_cap,
-                     m_dev, d, 4 * d, st)) != NRB_OK)
-      return rc;
+    if ((rc = latent_block_rows(w, f, xc, x_dtype, row_map, m_dev, rows_cap, h2, st)) != NRB_OK) return rc;
     if (packed) {
       const int gp = (int)std::min<int64_t>(items, (int64_t)sms * 16);
       pool_items_kernel<4><<<gp, 256, 0, st>>>(f.h2, d, f.item_off, seq, items, d, pooled_out + i0 * d); note_launch();
       NRB_CUDA_CHECK(cudaGetLastError());
     }
   }
+  return NRB_OK;
+}
+
+// Varlen entry: tokens already packed [n_tokens, dim] with CSR item offsets (device int32 [batch+1]); this is the
+// layout a packed token store hands over (the reference pads per batch: data_utils.py:878-933, 753-781).
+extern "C" int nrb_latent_forward_packed(const nrb_latent_weights* w, const void* x_packed, int x_dtype,
+                                         int64_t n_tokens, const int32_t* item_off, int64_t batch,
+                                         float* pooled_out, void* workspace, size_t workspace_bytes,
+                                         nrb_stream_t stream) {
+  NRB_REQUIRE(w != nullptr, "nrb_latent_forward_packed: null weights");
+  NRB_REQUIRE(w->precision == NRB_F32 || w->precision == NRB_BF16, "nrb_latent_forward_packed: bad precision");
+  NRB_REQUIRE(x_dtype == NRB_F32 || x_dtype == NRB_BF16, "nrb_latent_forward_packed: bad x dtype");
+  NRB_REQUIRE(n_tokens >= 0 && batch >= 0, "nrb_latent_forward_packed: bad sizes");
+  NRB_REQUIRE(w->dim % 64 == 0 && w->dim <= 4096, "nrb_latent_forward_packed: unsupported dim %d", w->dim);
+  if (batch == 0 || n_tokens == 0) return NRB_OK;
+  NRB_REQUIRE(x_packed && item_off && pooled_out && workspace, "nrb_latent_forward_packed: null pointer");
+  FwdWs f = fwd_ws(workspace, w, n_tokens, 1);
+  if (workspace_bytes < f.bytes) {
+    set_error("nrb_latent_forward_packed: workspace too small (%zu < %zu)", workspace_bytes, f.bytes);
+    return NRB_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = latent_block_rows(w, f, x_packed, x_dtype, nullptr, nullptr, n_tokens, f.h2, st)) != NRB_OK) return rc;
+  const int gp = (int)std::min<int64_t>(batch, (int64_t)sm_count_cached() * 16);
+  pool_items_kernel<4><<<gp, 256, 0, st>>>(f.h2, w->dim, item_off, 0, batch, w->dim, pooled_out); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
 }

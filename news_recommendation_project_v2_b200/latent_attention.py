@@ -89,6 +89,20 @@ class LatentAttentionModel(nn.Module):
         return self._folded
 
     @torch.no_grad()
+    def forward_packed(self, tokens: torch.Tensor, item_offsets: torch.Tensor) -> torch.Tensor:
+        """Varlen variant: `tokens` [T, d] holds only real tokens, `item_offsets` [B+1] their CSR offsets ->
+        [B, d] unit-norm vectors (the layout of a packed token store; no padding, no mask)."""
+        in_dev = tokens.device
+        dev = _lib.require_device(in_dev if in_dev.type == "cuda" else None)
+        fw = self.folded(None, dev)
+        with torch.cuda.device(dev):
+            x = tokens.detach().to(dev)
+            if x.dtype not in (torch.float32, torch.bfloat16):
+                x = x.float()
+            out = ops.latent_forward_packed(fw, x.contiguous(), item_offsets, max_tokens=config.LATENT_MAX_TOKENS)
+        return out if in_dev.type == "cuda" else out.to(in_dev)
+
+    @torch.no_grad()
     def forward(self, embeddings: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B,S,d] (+ mask [B,S]) -> [B,d] unit-norm, or un-pooled [B,S,d] when the mask is None."""
         if not self.output_normalize:

@@ -298,3 +298,34 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     check(load().nrb_layer_norm(ptr(x), dtype_code(x.dtype), x.stride(0), ptr(gamma), ptr(beta), float(eps), ptr(y),
                                 dtype_code(out_dtype), y.stride(0), rows, dim, stream_ptr()), "nrb_layer_norm")
     return y
+
+
+def latent_forward_packed(fw: FoldedLatent, tokens: torch.Tensor, item_off: torch.Tensor, max_tokens: int = 65536):
+    """Varlen latent-attention pooling: tokens [T, d] (packed, fp32/bf16), item_off int64/int32 [B+1] on the
+    host or device -> pooled [B, d] fp32.  Items are processed in chunks of at most `max_tokens` tokens."""
+    dev = require_device(tokens.device)
+    _dev(tokens, "tokens")
+    T, d = tokens.shape
+    if d != fw.dim:
+        raise _lib.NrbError(f"token dim {d} != model dim {fw.dim}")
+    off_host = item_off.detach().cpu().to(torch.int64)
+    B = off_host.numel() - 1
+    if int(off_host[-1]) != T or int(off_host[0]) != 0:
+        raise _lib.NrbError("item_off must start at 0 and end at the number of tokens")
+    lib = load()
+    max_tokens = max(int(max_tokens), int((off_host[1:] - off_host[:-1]).max()) if B else 1)
+    ws_bytes = lib.nrb_latent_forward_workspace_bytes(C.byref(fw.struct), max_tokens)
+    ws = _workspace(dev, ws_bytes)
+    out = torch.empty(B, d, dtype=torch.float32, device=dev)
+    i0 = 0
+    while i0 < B:
+        # largest item range [i0, i1) whose tokens fit the workspace
+        i1 = int(torch.searchsorted(off_host, off_host[i0] + max_tokens, right=True).item()) - 1
+        i1 = max(i1, i0 + 1)
+        t0, t1 = int(off_host[i0]), int(off_host[i1])
+        local_off = (off_host[i0:i1 + 1] - t0).to(torch.int32).to(dev)
+        check(lib.nrb_latent_forward_packed(C.byref(fw.struct), ptr(tokens[t0:t1]), dtype_code(tokens.dtype), t1 - t0,
+                                            ptr(local_off), i1 - i0, ptr(out[i0:i1]), ptr(ws), ws.numel(),
+                                            stream_ptr()), "nrb_latent_forward_packed")
+        i0 = i1
+    return out

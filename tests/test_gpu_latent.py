@@ -113,3 +113,25 @@ def test_refold_after_weight_update():
     assert not torch.equal(a, b)
     want = oracle.latent_pool(m.state_dict(), x, mask, heads=2, dim_head=64).float()
     np.testing.assert_allclose(b.cpu().numpy(), want.numpy(), atol=3e-6, rtol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_packed_equals_padded_forward(precision):
+    """Varlen entry (packed tokens + CSR offsets) == padded + masked forward, bit for bit; chunked by tokens."""
+    from news_recommendation_project_v2_b200 import config
+    m = _model(256, 64, 13, precision, heads=4, dim_head=64)
+    x, mask = syn.make_token_batch(29, 20, 256, seed=14, min_len=1)
+    want = m(x.cuda(), mask.cuda()).cpu()
+    lens = mask.sum(1)
+    off = torch.zeros(30, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens, 0)
+    packed = x[mask.bool()]
+    old = config.LATENT_MAX_TOKENS
+    try:
+        for mt in (20, 77, 65536):
+            config.LATENT_MAX_TOKENS = mt
+            got = m.forward_packed(packed.cuda(), off).cpu()
+            assert torch.equal(got, want)
+    finally:
+        config.LATENT_MAX_TOKENS = old
+    assert m.forward_packed(packed, off).device.type == "cpu"
