@@ -135,3 +135,23 @@ def test_forward_packed_equals_padded_forward(precision):
     finally:
         config.LATENT_MAX_TOKENS = old
     assert m.forward_packed(packed, off).device.type == "cpu"
+
+
+def test_apply_token_attn_from_token_store(tmp_path):
+    """Token store -> forward_packed == the reference flow (pad to batch max + mask + forward)."""
+    from news_recommendation_project_v2_b200.token_store import apply_token_attn, write_token_store
+    m = _model(256, 64, 21, "fp32", heads=4, dim_head=64)
+    g = torch.Generator().manual_seed(3)
+    items = [torch.randn(int(n), 256, generator=g).half() for n in torch.randint(1, 30, (37,), generator=g)]
+    db = str(tmp_path / "tok.sqlite")
+    write_token_store(db, items)
+    got = apply_token_attn(m, db, len(items), chunk_items=10)
+    S = max(t.shape[0] for t in items)
+    x = torch.zeros(len(items), S, 256)
+    mask = torch.zeros(len(items), S, dtype=torch.int32)
+    for i, t in enumerate(items):
+        x[i, :t.shape[0]] = t.float()
+        mask[i, :t.shape[0]] = 1
+    want = oracle.latent_pool(m.state_dict(), x, mask, heads=4, dim_head=64).float()
+    # bf16 token storage in read_token_store (default) vs fp16 source: compare at bf16 input precision
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-3, rtol=0)

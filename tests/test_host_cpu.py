@@ -184,3 +184,19 @@ def test_native_csr_builder_matches_reference(golden_dir):
     assert list(got["news_list"]) == list(want["news_list"]) and len(got["labels"]) == 0
     for key in ("impression_rev_ind_array", "impression_len_list", "history_rev_ind_array", "history_len_list"):
         assert np.array_equal(got[key], want[key])
+
+
+def test_token_store_roundtrip(tmp_path):
+    """sqlite token store (reference format) -> packed tokens + CSR offsets."""
+    from news_recommendation_project_v2_b200.token_store import read_token_store, write_token_store
+    g = torch.Generator().manual_seed(0)
+    items = [torch.randn(n, 16, generator=g).half() for n in (3, 1, 7, 2)]
+    db = str(tmp_path / "tok.sqlite")
+    write_token_store(db, items)
+    tokens, off = read_token_store(db, dtype=torch.float32)
+    assert off.tolist() == [0, 3, 4, 11, 13] and tokens.shape == (13, 16)
+    assert torch.equal(tokens[4:11], items[2].float())
+    tokens, off = read_token_store(db, ids=[2, 0, 2], dtype=torch.float32)
+    assert off.tolist() == [0, 7, 10, 17] and torch.equal(tokens[7:10], items[0].float())
+    with pytest.raises(IndexError):
+        read_token_store(db, ids=[9])
