@@ -86,6 +86,10 @@ int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, int dim, in
  *                     for FINAL_ATTENTION they are the separable per-row outputs
  *                     x and exp(logit) of nrb_final_attention_rows.
  *   cand            : the table candidates are scored against (news_embeddings).
+ *   cand_base/alpha : optional fp32 [n_rows] per-row baseline (the classification head's score) blended behind
+ *                     the cosine like WeightedSumModel (modeling_utils.py:158-165): alpha*cos + (1-alpha)*base;
+ *                     impressions with an empty history get `base` alone (data_model_helper.py:284-299).
+ *                     NULL = pure cosine.
  *   *_off           : int64 CSR offsets [n_imp + 1] into hist_idx / cand_idx.
  *   user_out        : optional fp32 [n_imp, dim] (NULL to skip).
  *   scores          : fp32 [cand_off[n_imp]] (absolute candidate positions).
@@ -94,6 +98,7 @@ int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, int dim, in
 int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
                    const void* hist_x, const void* hist_e, int64_t hist_stride,
                    const void* cand, int64_t cand_stride,
+                   const float* cand_base, float blend_alpha,
                    const int32_t* hist_idx, const int64_t* hist_off,
                    const int32_t* cand_idx, const int64_t* cand_off, int64_t n_imp,
                    float* user_out, float* scores, int32_t* ranks, int32_t* err_flag,

@@ -53,6 +53,8 @@ struct ScoreRankParams {
   const char* hist_x;
   const char* hist_e;
   const char* cand;
+  const float* cand_base;  // optional per-row baseline score blended into the cosine (NULL = pure cosine)
+  float alpha;             // blended = alpha * cosine + (1 - alpha) * base; impressions without history: base
   int64_t hist_stride_bytes;
   int64_t cand_stride_bytes;
   const int32_t* hist_idx;
@@ -209,9 +211,11 @@ score_rank_kernel(const ScoreRankParams p) {
       constexpr int CR = (16 / NV) > 0 ? (16 / NV) : 1;  // candidate rows in flight per iteration
       for (int s = 0; s < cnt; s += CR) {
         uint4 a[CR][NV];
+        int rr[CR];
 #pragma unroll
         for (int q = 0; q < CR; ++q) {
           const int r = __shfl_sync(kFullMask, my, min(s + q, cnt - 1));
+          rr[q] = r;
           load_row<T, NV>(p.cand + (int64_t)r * p.cand_stride_bytes, lane, a[q]);
         }
         __syncwarp();  // all loads issued before the first use (see the history loop)
@@ -241,7 +245,13 @@ score_rank_kernel(const ScoreRankParams p) {
         }
 #pragma unroll
         for (int q = 0; q < CR; ++q) {
-          const float sc = dot[q] / fmaxf(sqrtf(sq[q]), 1e-8f);
+          float sc = dot[q] / fmaxf(sqrtf(sq[q]), 1e-8f);
+          if (p.cand_base != nullptr) {
+            // WeightedSumModel (modeling_utils.py:158-165) fused behind the cosine; rows without history keep
+            // the classification baseline alone (data_model_helper.py:284-299)
+            const float base = p.cand_base[rr[q]];
+            sc = (h1 > h0) ? sc * p.alpha + base * (1.0f - p.alpha) : base;
+          }
           if (lane == s + q) my_score = sc;
         }
       }
@@ -388,7 +398,7 @@ extern "C" int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, 
 
 extern "C" int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows, const void* hist_x,
                               const void* hist_e, int64_t hist_stride, const void* cand, int64_t cand_stride,
-                              const int32_t* hist_idx, const int64_t* hist_off, const int32_t* cand_idx,
+                              const float* cand_base, float blend_alpha, const int32_t* hist_idx, const int64_t* hist_off, const int32_t* cand_idx,
                               const int64_t* cand_off, int64_t n_imp, float* user_out, float* scores,
                               int32_t* ranks, int32_t* err_flag, nrb_stream_t stream) {
   NRB_REQUIRE(dtype == NRB_F32 || dtype == NRB_BF16, "nrb_score_rank: bad dtype %d", dtype);
@@ -408,6 +418,8 @@ extern "C" int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
   p.hist_x = (const char*)hist_x;
   p.hist_e = (const char*)hist_e;
   p.cand = (const char*)cand;
+  p.cand_base = cand_base;
+  p.alpha = blend_alpha;
   p.hist_stride_bytes = hist_stride * es;
   p.cand_stride_bytes = cand_stride * es;
   p.hist_idx = hist_idx;

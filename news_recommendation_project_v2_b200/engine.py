@@ -240,17 +240,24 @@ class ScoringEngine:
         return (_as_i32(hist_idx, self.device), h_off, _as_i32(cand_idx, self.device), c_off, n_c)
 
     def score_device(self, hist_idx_d, hist_off_d, cand_idx_d, cand_off_d, n_cand: int, want_user=False,
-                     want_ranks=True, err_flag=None, out_scores=None, out_ranks=None):
+                     want_ranks=True, err_flag=None, out_scores=None, out_ranks=None, cand_base=None,
+                     blend_alpha: float = 1.0):
         with torch.cuda.device(self.device):
             return ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hist_idx_d, hist_off_d,
                                   cand_idx_d, cand_off_d, n_cand, want_user=want_user, want_ranks=want_ranks,
-                                  err_flag=err_flag, out_scores=out_scores, out_ranks=out_ranks)
+                                  err_flag=err_flag, out_scores=out_scores, out_ranks=out_ranks, cand_base=cand_base,
+                                  blend_alpha=blend_alpha)
 
-    def score(self, hist_idx, hist_len, cand_idx, cand_len, want_user=False, want_ranks=True):
-        """Host arrays in, device tensors out: (user|None, scores fp32, ranks int32|None)."""
+    def score(self, hist_idx, hist_len, cand_idx, cand_len, want_user=False, want_ranks=True, cand_base=None,
+              blend_alpha: float = 1.0):
+        """Host arrays in, device tensors out: (user|None, scores fp32, ranks int32|None).
+        `cand_base` (fp32 per table row) + `blend_alpha` fuse the WeightedSumModel blend behind the cosine."""
         with torch.cuda.device(self.device):
             hi, ho, ci, co, n_c = self.upload_impressions(hist_idx, hist_len, cand_idx, cand_len)
-            return self.score_device(hi, ho, ci, co, n_c, want_user=want_user, want_ranks=want_ranks)
+            if cand_base is not None:
+                cand_base = torch.as_tensor(cand_base, dtype=torch.float32).to(self.device).contiguous()
+            return self.score_device(hi, ho, ci, co, n_c, want_user=want_user, want_ranks=want_ranks,
+                                     cand_base=cand_base, blend_alpha=blend_alpha)
 
     def user_vectors(self, hist_idx, hist_len) -> torch.Tensor:
         """get_final_attention_eval: fp32 [I, d] user vectors (device)."""

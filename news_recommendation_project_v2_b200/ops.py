@@ -71,8 +71,9 @@ def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tens
                hist_idx: torch.Tensor, hist_off: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
                n_cand_total: int, want_user: bool = False, want_ranks: bool = True,
                err_flag: Optional[torch.Tensor] = None, out_scores: Optional[torch.Tensor] = None,
-               out_ranks: Optional[torch.Tensor] = None):
-    """Fused gather -> user vector -> cosine -> dense rank (nrb_score_rank)."""
+               out_ranks: Optional[torch.Tensor] = None, cand_base: Optional[torch.Tensor] = None,
+               blend_alpha: float = 1.0):
+    """Fused gather -> user vector -> cosine (-> blend with a per-row baseline) -> dense rank (nrb_score_rank)."""
     dev = require_device(hist_x.device)
     _dev(hist_x, "hist_x")
     _dev(cand, "cand", hist_x.dtype)
@@ -93,10 +94,14 @@ def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tens
     ranks = None
     if want_ranks:
         ranks = out_ranks if out_ranks is not None else torch.empty(max(n_cand_total, 1), dtype=torch.int32, device=dev)
+    if cand_base is not None:
+        _dev(cand_base, "cand_base", torch.float32)
+        if cand_base.numel() < n_rows:
+            raise _lib.NrbError("cand_base must have one entry per table row")
     flag = err_flag if err_flag is not None else new_err_flag(dev)
     check(load().nrb_score_rank(pool_mode, dtype_code(hist_x.dtype), dim, min(n_rows, hist_x.shape[0]),
                                 ptr(hist_x), ptr(hist_e), hist_x.stride(0), ptr(cand), cand.stride(0),
-                                ptr(hist_idx), ptr(hist_off), ptr(cand_idx), ptr(cand_off), n_imp,
+                                ptr(cand_base), float(blend_alpha), ptr(hist_idx), ptr(hist_off), ptr(cand_idx), ptr(cand_off), n_imp,
                                 ptr(user), ptr(scores), ptr(ranks), ptr(flag), stream_ptr()), "nrb_score_rank")
     if err_flag is None:
         raise_on_index_error(flag, "score_rank")

@@ -102,6 +102,37 @@ def golden_new_attention(ref):
     print("new_attention", out.shape)
 
 
+def golden_final_score(ref):
+    """get_final_score (data_model_helper.py:272-301): ClassificationHead baseline + FinalAttention cosine blended by
+    WeightedSumModel, with a mix of impressions with / without history."""
+    dim, hidden, n_rows, n_imp, seed = 256, 512, 1500, 40, 321
+    mu, dmh = ref.modeling_utils, ref.data_model_helper
+    torch.manual_seed(seed)
+    head = mu.ClassificationHead(in_dim=dim, hidden_dim=dim, out_dim=1).eval()
+    attn = ref_harness.make_reference_final_attention(ref, dim, hidden, seed=seed)
+    attn.load_state_dict(syn.make_final_attention_state_dict(dim, hidden, seed=seed))
+    wsum = mu.WeightedSumModel()
+    with torch.no_grad():
+        wsum.alpha.fill_(0.7)
+    table = syn.make_table(n_rows, dim, seed=seed + 1)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=20, cand="small", seed=seed + 2)
+    hb = np.ones(n_imp, dtype=bool)
+    hb[[3, 4, 17, 30]] = False
+    h_off = syn.csr_offsets(imp.hist_len)
+    hist_idx = np.concatenate([imp.hist_idx[h_off[i]:h_off[i + 1]] for i in range(n_imp) if hb[i]])
+    hist_len = imp.hist_len[hb]
+    old_dev = dmh.DEVICE
+    with torch.no_grad():
+        cls = dmh.get_classification_preds(table, head)
+        out = dmh.get_final_score(hist_idx, hist_len, imp.cand_idx, imp.cand_len, table, cls, pd.Series(hb), attn, wsum)
+    np.savez_compressed(os.path.join(GOLD, "final_score_blend_d256.npz"), dim=dim, hidden=hidden, n_rows=n_rows,
+                        n_imp=n_imp, seed=seed, history_bool=hb, classification=cls.astype(np.float32),
+                        scores=np.asarray(out["scores"], dtype=np.float32),
+                        ranks=np.concatenate([np.asarray(r, dtype=np.float64) for r in out["grouped_scores"]]),
+                        **{"head::" + k: v.numpy() for k, v in head.state_dict().items()})
+    print("final_score_blend", out["scores"].shape)
+
+
 def golden_small(ref):
     du = ref.data_utils
     # collate (data_utils.py:784-791)
@@ -140,6 +171,7 @@ def main():
     ref = ref_harness.load_reference(batch_size=16)
     golden_small(ref)
     golden_new_attention(ref)
+    golden_final_score(ref)
     golden_latent(ref, "latent_cfg1_d768_L512", 768, 512, 32, 64, seed=1234)
     golden_latent(ref, "latent_default_d1024_L64", 1024, 64, 4, 16, seed=4321)
     golden_final(ref, "final_small_d768", 768, 4096, 4096, 64, "small", seed=1234)

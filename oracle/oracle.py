@@ -261,6 +261,30 @@ def final_second_attention_score(sd: dict, table: torch.Tensor, hist_idx, hist_l
     return {"user": u, "scores": s_np, "grouped_scores": rank_group_preds(s_np, cand_len)}
 
 
+def classification_head(sd: dict, rows: torch.Tensor, dtype=torch.float64) -> torch.Tensor:
+    """ClassificationHead.forward (modeling_utils.py:106-116): linear_3(relu(linear_2(relu(linear_1(e)))))."""
+    g = lambda k: sd[k].detach().to(dtype)
+    x = torch.relu(rows.to(dtype) @ g("linear_1.weight").T + g("linear_1.bias"))
+    x = torch.relu(x @ g("linear_2.weight").T + g("linear_2.bias"))
+    return x @ g("linear_3.weight").T + g("linear_3.bias")
+
+
+def final_score(sd: dict, table: torch.Tensor, hist_idx, hist_len, cand_idx, cand_len, history_bool,
+                classification_score: np.ndarray, alpha_param: float, dtype=torch.float64):
+    """get_final_score (data_model_helper.py:272-301) with FinalAttention as the attention model:
+    scores = classification_score[cand]; rows with history are overwritten by
+    sigmoid(alpha)*cos + (1-sigmoid(alpha))*classification_score[cand] (WeightedSumModel, modeling_utils.py:158-165)."""
+    hb = np.asarray(history_bool, dtype=bool)
+    cand_len = np.asarray(cand_len)
+    scores = np.asarray(classification_score, dtype=np.float64)[np.asarray(cand_idx)].copy()
+    keep = np.repeat(hb, cand_len)
+    u = user_vectors(sd, table, hist_idx, hist_len, dtype=dtype)
+    cos = cosine_scores(u, table, np.asarray(cand_idx)[keep], cand_len[hb], dtype=dtype).numpy()
+    a = 1.0 / (1.0 + math.exp(-alpha_param))
+    scores[keep] = cos * a + scores[keep] * (1.0 - a)
+    return {"scores": scores, "grouped_scores": rank_group_preds(scores, cand_len)}
+
+
 # --------------------------------------------------------------------------
 # Consumer -- MIND metrics (evaluation.py:13-98)
 # --------------------------------------------------------------------------

@@ -245,3 +245,41 @@ def test_new_attention_arm(golden_dir, precision, tol):
     u = oracle.new_attention(sd, emb, msk)
     want = oracle.cosine_scores(u, table, imp.cand_idx, imp.cand_len).numpy()
     np.testing.assert_allclose(sc.numpy(), want, atol=1e-5 if precision == "fp32" else 5e-3, rtol=0)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_final_score_blend_and_classification_head(golden_dir, precision, tol):
+    """get_final_score (data_model_helper.py:272-301): classification baseline + cosine blended inside the fused
+    score/rank kernel, no-history impressions fall back to the baseline."""
+    from tests.test_oracle_golden import _final_score_fixture
+    from news_recommendation_project_v2_b200.data_model_helper import (get_classification_preds, get_final_score,
+                                                                       get_final_only_attention_score)
+    from news_recommendation_project_v2_b200.modeling_utils import ClassificationHead, WeightedSumModel
+    g, head_sd, attn_sd, table, imp, hb, hist_idx, hist_len = _final_score_fixture(golden_dir)
+    dim, hidden = int(g["dim"]), int(g["hidden"])
+    head = ClassificationHead(dim, dim, 1, precision=precision).eval()
+    head.load_state_dict(head_sd, strict=True)
+    cls = get_classification_preds(table, head)
+    np.testing.assert_allclose(cls, g["classification"], atol=tol * 2, rtol=tol)
+    attn = _final_model(dim, hidden, int(g["seed"]), precision)
+    wsum = WeightedSumModel()
+    with torch.no_grad():
+        wsum.alpha.fill_(0.7)
+    # feed the REFERENCE's baseline so that only the fused blend / cosine / rank are under test
+    out = get_final_score(hist_idx, hist_len, imp.cand_idx, imp.cand_len, table, g["classification"], hb, attn, wsum,
+                          precision=precision)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=tol, rtol=0)
+    ranks = np.concatenate([np.asarray(r) for r in out["grouped_scores"]])
+    assert np.array_equal(ranks, np.concatenate(oracle.rank_group_preds(out["scores"], imp.cand_len)))
+    if precision == "fp32":
+        hard, soft = _rank_mismatches(ranks, g["ranks"], g["scores"], imp.cand_len, gap=1e-5)
+        assert hard == 0 and soft <= 1
+    # impressions without history carry the baseline bit for bit
+    off = syn.csr_offsets(imp.cand_len)
+    for i in np.flatnonzero(~hb):
+        assert np.array_equal(out["scores"][off[i]:off[i + 1]], g["classification"][imp.cand_idx[off[i]:off[i + 1]]])
+    only = get_final_only_attention_score(hist_idx, hist_len, imp.cand_idx, imp.cand_len, table, g["classification"],
+                                          hb, attn, precision=precision)
+    want = oracle.final_score(attn_sd, table, hist_idx, hist_len, imp.cand_idx, imp.cand_len, hb, g["classification"],
+                              alpha_param=60.0)["scores"]  # sigmoid(60) == 1: pure cosine where there is history
+    np.testing.assert_allclose(only["scores"], want, atol=tol, rtol=0)

@@ -48,9 +48,9 @@ def test_argument_validation_without_gpu():
     """Bad shapes are rejected by the library before any CUDA call."""
     from news_recommendation_project_v2_b200 import _lib
     lib = _lib.load()
-    rc = lib.nrb_score_rank(0, 1, 100, 10, 1, 1, 100, 1, 100, 1, 1, 1, 1, 4, None, 1, None, 1, None)
+    rc = lib.nrb_score_rank(0, 1, 100, 10, 1, 1, 100, 1, 100, None, 1.0, 1, 1, 1, 1, 4, None, 1, None, 1, None)
     assert rc == -1 and b"multiple of 512" in lib.nrb_last_error()
-    rc = lib.nrb_score_rank(7, 1, 256, 10, 1, 1, 256, 1, 256, 1, 1, 1, 1, 4, None, 1, None, 1, None)
+    rc = lib.nrb_score_rank(7, 1, 256, 10, 1, 1, 256, 1, 256, None, 1.0, 1, 1, 1, 1, 4, None, 1, None, 1, None)
     assert rc == -1 and b"pool_mode" in lib.nrb_last_error()
     assert lib.nrb_dense_rank(None, None, 0, None, None) == 0  # empty problem is a no-op
     assert lib.nrb_final_attention_rows_workspace_bytes(1, 161013, 1024, 4096) > 2 * 16384 * 4096 * 2

@@ -145,3 +145,26 @@ def test_new_attention_matches_reference(golden_dir):
     g, sd, emb, msk, _, _ = _new_attention_fixture(golden_dir)
     out = oracle.new_attention(sd, emb, msk, num_layers=1, dtype=torch.float64).float().numpy()
     np.testing.assert_allclose(out, g["out"], atol=3e-6, rtol=1e-5)
+
+
+def _final_score_fixture(golden_dir):
+    g = _load(golden_dir, "final_score_blend_d256")
+    dim, hidden, n_rows, n_imp, seed = (int(g[k]) for k in ("dim", "hidden", "n_rows", "n_imp", "seed"))
+    head_sd = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("head::")}
+    attn_sd = syn.make_final_attention_state_dict(dim, hidden, seed=seed)
+    table = syn.make_table(n_rows, dim, seed=seed + 1)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=20, cand="small", seed=seed + 2)
+    hb = g["history_bool"]
+    h_off = syn.csr_offsets(imp.hist_len)
+    hist_idx = np.concatenate([imp.hist_idx[h_off[i]:h_off[i + 1]] for i in range(n_imp) if hb[i]])
+    return g, head_sd, attn_sd, table, imp, hb, hist_idx, imp.hist_len[hb]
+
+
+def test_final_score_blend_matches_reference(golden_dir):
+    g, head_sd, attn_sd, table, imp, hb, hist_idx, hist_len = _final_score_fixture(golden_dir)
+    cls = oracle.classification_head(head_sd, table).squeeze(-1).numpy()
+    np.testing.assert_allclose(cls, g["classification"], atol=2e-6, rtol=1e-5)
+    out = oracle.final_score(attn_sd, table, hist_idx, hist_len, imp.cand_idx, imp.cand_len, hb, g["classification"],
+                             alpha_param=0.7)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=2e-6, rtol=0)
+    assert np.array_equal(np.concatenate(oracle.rank_group_preds(g["scores"], imp.cand_len)), g["ranks"])
