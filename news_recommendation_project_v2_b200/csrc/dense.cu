@@ -260,17 +260,18 @@ int scale_cols_f32(float* x, int64_t ld, int64_t rows, int cols, float s, cudaSt
 }
 
 int linear(int precision, int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
-           const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
-           int N, int K, cudaStream_t st, int group, int group_valid) {
+           const float* bias, const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
+           int N, int K, cudaStream_t st, int group, int group_valid, int res_dtype, const int32_t* res_map) {
   if (precision == NRB_BF16)
     return gemm_bf16_tc(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, group,
-                        group_valid, st);
+                        group_valid, st, res_dtype, res_map);
   if (precision == NRB_F32 && epi == NRB_EPI_SOFTMAX) {
     set_error("nrb_linear(fp32): the fused softmax epilogue exists only on the tensor-core path");
     return NRB_E_INVALID;
   }
   if (precision == NRB_F32)
-    return gemm_f32_simt(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st);
+    return gemm_f32_simt(epi, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, m_dev, N, K, st, res_dtype,
+                         res_map);
   set_error("nrb_linear: bad precision %d", precision);
   return NRB_E_INVALID;
 }

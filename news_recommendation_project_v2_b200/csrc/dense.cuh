@@ -7,17 +7,20 @@ namespace nrb {
 
 // gemm_tc.cu -- tcgen05 / TMA / TMEM (bf16 operands)
 int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
-                 const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev, int N, int K,
-                 int group, int group_valid, cudaStream_t st);
+                 const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev, int N, int K,
+                 int group, int group_valid, cudaStream_t st, int res_dtype = NRB_F32,
+                 const int32_t* res_map = nullptr);
 // gemm_simt.cu -- FFMA (fp32 operands)
 int gemm_f32_simt(int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
-                  const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M,
-                  const int* m_dev, int N, int K, cudaStream_t st);
+                  const float* bias, const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M,
+                  const int* m_dev, int N, int K, cudaStream_t st, int res_dtype = NRB_F32,
+                  const int32_t* res_map = nullptr);
 
 // precision-dispatching linear
 int linear(int precision, int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
-           const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
-           int N, int K, cudaStream_t st, int group = 0, int group_valid = 0);
+           const float* bias, const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev,
+           int N, int K, cudaStream_t st, int group = 0, int group_valid = 0, int res_dtype = NRB_F32,
+           const int32_t* res_map = nullptr);
 
 // dense.cu -- row-wise helpers (all take an optional device-side row count)
 int layer_norm_rows(const void* x, int x_dtype, int64_t ldx, const int32_t* row_map, const float* gamma,

@@ -22,7 +22,9 @@ struct SimtParams {
   const float* w;
   int64_t ldw;
   const float* bias;
-  const float* res;
+  const void* res;
+  int res_dtype;
+  const int32_t* res_map;
   int64_t ldres;
   void* y;
   int64_t ldy;
@@ -131,11 +133,21 @@ gemm_simt_kernel(const SimtParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = expf(v[q]);
       } else if (EPI == NRB_EPI_RESIDUAL) {
-        const float4 r = *reinterpret_cast<const float4*>(p.res + row * p.ldres + col);
-        v[0] += r.x;
-        v[1] += r.y;
-        v[2] += r.z;
-        v[3] += r.w;
+        const int64_t arow = p.row_base + row;  // row maps are indexed by the absolute row
+        const int64_t rrow = p.res_map != nullptr ? (int64_t)p.res_map[arow] : row;
+        if (p.res_dtype == NRB_F32) {
+          const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + rrow * p.ldres + col);
+          v[0] += r.x;
+          v[1] += r.y;
+          v[2] += r.z;
+          v[3] += r.w;
+        } else {
+          const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow * p.ldres + col);
+          v[0] += bf16_lo(r.x);
+          v[1] += bf16_hi(r.x);
+          v[2] += bf16_lo(r.y);
+          v[3] += bf16_hi(r.y);
+        }
       }
       if (EPI == NRB_EPI_GEGLU) {
         const float o0 = v[0] * gelu_erf_f32(v[1]);
@@ -179,8 +191,8 @@ static int dispatch_simt(int epi, const SimtParams& p, dim3 grid, cudaStream_t s
 }
 
 int gemm_f32_simt(int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw,
-                  const float* bias, const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M,
-                  const int* m_dev, int N, int K, cudaStream_t st) {
+                  const float* bias, const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M,
+                  const int* m_dev, int N, int K, cudaStream_t st, int res_dtype, const int32_t* res_map) {
   NRB_REQUIRE(M > 0 && N > 0 && K > 0, "nrb_linear: empty problem");
   NRB_REQUIRE(K % SBK == 0, "nrb_linear(fp32): K must be a multiple of 16 (got %d)", K);
   NRB_REQUIRE(N % 4 == 0, "nrb_linear(fp32): N must be a multiple of 4 (got %d)", N);
@@ -197,6 +209,8 @@ int gemm_f32_simt(int epi, int out_dtype, const void* a, int64_t lda, const void
   p.ldw = ldw;
   p.bias = bias;
   p.res = res;
+  p.res_dtype = res_dtype;
+  p.res_map = res_map;
   p.ldres = ldres;
   p.y = y;
   p.ldy = ldy;
@@ -213,7 +227,8 @@ int gemm_f32_simt(int epi, int out_dtype, const void* a, int64_t lda, const void
     SimtParams q = p;
     const int64_t rows0 = y0 * SBM;
     q.a = p.a + rows0 * lda;
-    if (p.res) q.res = p.res + rows0 * ldres;
+    if (p.res && p.res_map == nullptr)
+      q.res = (const char*)p.res + (size_t)rows0 * ldres * (res_dtype == NRB_F32 ? 4 : 2);
     q.y = out_dtype == NRB_BF16 ? (void*)((__nv_bfloat16*)p.y + rows0 * ldy) : (void*)((float*)p.y + rows0 * ldy);
     q.M = std::min<int64_t>(M - rows0, max_y * SBM);
     q.row_base = rows0;

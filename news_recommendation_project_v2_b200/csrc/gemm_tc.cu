@@ -70,7 +70,9 @@ struct GemmParams {
   const int* m_dev;  // optional device-side row count (varlen token packing, no host sync)
   int N, K;
   const float* bias;
-  const float* res;
+  const void* res;          // residual operand: fp32 or bf16 rows ...
+  int res_dtype;            // NRB_F32 | NRB_BF16
+  const int32_t* res_map;   // ... optionally gathered through a row map (varlen token packing: res = the raw input)
   int64_t ldres;
   void* y;  // direct-store epilogues only
   int64_t ldy;
@@ -130,14 +132,27 @@ __device__ __forceinline__ void activate_chunk(const uint32_t (&acc)[32], const 
     for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j] * kLog2e);
   } else if (EPI == NRB_EPI_RESIDUAL) {
     if (row_ok) {
-      const float* r = p.res + row * p.ldres + col0;
+      const int64_t rrow = p.res_map != nullptr ? (int64_t)p.res_map[row] : row;
+      if (p.res_dtype == NRB_F32) {
+        const float* r = reinterpret_cast<const float*>(p.res) + rrow * p.ldres + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(r + j);
-        v[j] += b.x;
-        v[j + 1] += b.y;
-        v[j + 2] += b.z;
-        v[j + 3] += b.w;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(r + j);
+          v[j] += b.x;
+          v[j + 1] += b.y;
+          v[j + 2] += b.z;
+          v[j + 3] += b.w;
+        }
+      } else {
+        const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow * p.ldres + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 b = *reinterpret_cast<const uint4*>(r + j);
+          float f[8];
+          Vec16<__nv_bfloat16>::unpack(b, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[j + k] += f[k];
+        }
       }
     }
   } else if (EPI == NRB_EPI_GEGLU) {
@@ -663,8 +678,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mw, c
 
 // y = epi(a @ w^T + bias); a [M,K] bf16, w [N,K] bf16.
 int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
-                 const float* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev, int N, int K,
-                 int group, int group_valid, cudaStream_t st) {
+                 const void* res, int64_t ldres, void* y, int64_t ldy, int64_t M, const int* m_dev, int N, int K,
+                 int group, int group_valid, cudaStream_t st, int res_dtype, const int32_t* res_map) {
   NRB_REQUIRE(M > 0 && N > 0 && K > 0, "nrb_linear: empty problem");
   NRB_REQUIRE(K % kBK == 0, "nrb_linear(bf16): K must be a multiple of 64 (got %d)", K);
   NRB_REQUIRE(N % 32 == 0, "nrb_linear(bf16): N must be a multiple of 32 (got %d)", N);
@@ -673,7 +688,8 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   const int64_t ycols_align = out_dtype == NRB_BF16 ? 8 : 4;
   NRB_REQUIRE(ldy % ycols_align == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
               "nrb_linear: y must be 16-byte aligned with a 16-byte multiple row pitch");
-  NRB_REQUIRE(res == nullptr || (ldres % 4 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0),
+  NRB_REQUIRE(res == nullptr || (ldres % (res_dtype == NRB_BF16 ? 8 : 4) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(res) & 15) == 0),
               "nrb_linear: res must be 16-byte aligned");
   NRB_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "nrb_linear: bias alignment");
   const bool softmax = epi == NRB_EPI_SOFTMAX;
@@ -714,6 +730,8 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   p.K = K;
   p.bias = bias;
   p.res = res;
+  p.res_dtype = res_dtype;
+  p.res_map = res_map;
   p.ldres = ldres;
   p.y = y;
   p.ldy = ldy;

@@ -170,7 +170,7 @@ static FoldWs fold_ws(void* base, int dim, int heads, int dim_head, int L) {
 struct FwdWs {
   int32_t *counts, *item_off, *m_dev, *row_map;
   void *xn, *p, *hn, *g;
-  float *xres, *logits, *h1, *h2;
+  float *logits, *h1, *h2;
   size_t bytes;
 };
 static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens, int64_t cap_items) {
@@ -183,7 +183,6 @@ static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens,
   f.m_dev = (int32_t*)ws.take(16);
   f.row_map = (int32_t*)ws.take((size_t)cap_tokens * 4);
   f.xn = ws.take((size_t)cap_tokens * w->dim * es);
-  f.xres = (float*)ws.take((size_t)cap_tokens * w->dim * 4);
   f.logits = (float*)ws.take((size_t)cap_tokens * hl * 4);
   f.p = ws.take((size_t)cap_tokens * hl * es);
   f.h1 = (float*)ws.take((size_t)cap_tokens * w->dim * 4);
@@ -256,8 +255,8 @@ static int latent_block_rows(const nrb_latent_weights* w, const FwdWs& f, const 
   const int d = w->dim, P = w->precision;
   const int hl = w->heads * w->latents_padded;
   int rc;
-    // xn = LN1(x) (packed), xres = x (fp32)                      latent_attention.py:16
-    if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, f.xres, d, rows_cap, m_dev, d,
+    // xn = LN1(x), gathered through the row map when tokens are packed      latent_attention.py:16
+    if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, nullptr, 0, rows_cap, m_dev, d,
                               st)) != NRB_OK)
       return rc;
     // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
@@ -275,8 +274,9 @@ static int latent_block_rows(const nrb_latent_weights* w, const FwdWs& f, const 
         return rc;
     }
     // h1 = P B^T + x                                               :74, :162
-    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, f.xres, d, f.h1, d, rows_cap, m_dev,
-                     d, hl, st)) != NRB_OK)
+    // (the residual operand is the RAW input row, read in place through the same row map: no fp32 copy)
+    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, xc, d, f.h1, d, rows_cap, m_dev, d, hl,
+                     st, 0, 0, x_dtype, row_map)) != NRB_OK)
       return rc;
     // hn = LN2(h1)                                                 :16 (second PreNorm)
     if ((rc = layer_norm_rows(f.h1, NRB_F32, d, nullptr, w->ln2_w, w->ln2_b, f.hn, P, d, nullptr, 0, rows_cap, m_dev,
