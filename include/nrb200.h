@@ -69,6 +69,14 @@ long long nrb_kernel_launches(void);
 int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups,
                    int32_t* ranks, nrb_stream_t stream);
 
+/* ---- Stage C: per-impression top-k ordering --------------------------------------------------
+ * the order evaluation.py:14,28 derives from the ranks (argsort of the scores, descending), made
+ * explicit: out_idx[g, p] = position inside group g of the candidate at place p (p < k), equal scores in
+ * their original order (np.argsort(-scores, kind="stable")[:k]), -1 where the group has fewer than k
+ * candidates, NaN scores last.  out_idx is int32 [n_groups, k]. */
+int nrb_topk_order(const float* scores, const int64_t* offsets, int64_t n_groups, int k,
+                   int32_t* out_idx, nrb_stream_t stream);
+
 /* ---- Stage B: padded history gather -----------------------------------------------
  * replaces data_utils.py:784-791 final_attention_eval_collate_fn (+ pad_to_maxlen
  * :723-750): emb_out[g, s, :] = table[idx[offsets[g]+s], :] for s < len_g else 0;

@@ -327,6 +327,43 @@ dense_rank_kernel(const float* scores, const int64_t* offsets, int64_t n_groups,
   }
 }
 
+// ---- warp-level top-k ordering ---------------------------------------------------------------------
+// out[g, p] = position (within the group) of the candidate at place p of the descending order, p < k;
+// equal scores keep their original order (== np.argsort(-scores, kind="stable")[:k]); -1 pads groups
+// shorter than k.  NaN scores sort last.  One warp per group; place(j) = #{s_i > s_j} + #{i < j : s_i == s_j}.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+topk_order_kernel(const float* scores, const int64_t* offsets, int64_t n_groups, int k, int32_t* out) {
+  __shared__ float s_scores[kWarpsPerCta][kRankCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += stride) {
+    const int64_t c0 = offsets[g];
+    const int n = (int)(offsets[g + 1] - c0);
+    const bool in_smem = n <= kRankCap;
+    if (in_smem) {
+      for (int i = lane; i < n; i += 32) s_scores[warp][i] = scores[c0 + i];
+      __syncwarp();
+    }
+    const float* s = in_smem ? s_scores[warp] : scores + c0;
+    for (int p = lane; p < k; p += 32) out[g * k + p] = -1;
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+      const float v = s[j];
+      const bool vnan = v != v;
+      int place = 0;
+      for (int i = 0; i < n; ++i) {
+        const float u = s[i];
+        const bool unan = u != u;
+        // u sorts before v: larger, or equal and earlier; NaNs after every number, among themselves by position
+        const bool before = vnan ? (!unan || i < j) : (!unan && (u > v || (u == v && i < j)));
+        place += before;
+      }
+      if (place < k) out[g * k + place] = j;
+    }
+    __syncwarp();
+  }
+}
+
 // ---- padded gather (final_attention_eval_collate_fn drop-in) -----------------------------------
 // one warp per (group, slot): copies one table row (or zeros) with 128-bit accesses.
 __global__ void __launch_bounds__(256)
@@ -372,6 +409,19 @@ extern "C" int nrb_dense_rank(const float* scores, const int64_t* offsets, int64
   const int64_t want = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
   dense_rank_kernel<<<grid, kWarpsPerCta * 32, 0, as_stream(stream)>>>(scores, offsets, n_groups, ranks); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
+extern "C" int nrb_topk_order(const float* scores, const int64_t* offsets, int64_t n_groups, int k, int32_t* out_idx,
+                              nrb_stream_t stream) {
+  NRB_REQUIRE(n_groups >= 0 && k >= 1, "nrb_topk_order: bad sizes");
+  if (n_groups == 0) return NRB_OK;
+  NRB_REQUIRE(scores && offsets && out_idx, "nrb_topk_order: null pointer");
+  const int64_t want = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
+  topk_order_kernel<<<grid, kWarpsPerCta * 32, 0, as_stream(stream)>>>(scores, offsets, n_groups, k, out_idx);
+  note_launch();
   NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
 }

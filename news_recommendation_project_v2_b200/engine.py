@@ -259,6 +259,11 @@ class ScoringEngine:
             return self.score_device(hi, ho, ci, co, n_c, want_user=want_user, want_ranks=want_ranks,
                                      cand_base=cand_base, blend_alpha=blend_alpha)
 
+    def topk(self, scores_d: torch.Tensor, cand_off_d: torch.Tensor, k: int) -> torch.Tensor:
+        """Positions of the k best candidates of every impression (int32 [I, k], -1 padded), from device scores."""
+        with torch.cuda.device(self.device):
+            return ops.topk_order(scores_d, cand_off_d, k)
+
     def user_vectors(self, hist_idx, hist_len) -> torch.Tensor:
         """get_final_attention_eval: fp32 [I, d] user vectors (device)."""
         with torch.cuda.device(self.device):

@@ -47,6 +47,18 @@ def dense_rank(scores: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     return ranks
 
 
+def topk_order(scores: torch.Tensor, offsets: torch.Tensor, k: int) -> torch.Tensor:
+    """int32 [n_groups, k]: positions of each group's k best candidates in descending score order (stable),
+    -1 padded (nrb_topk_order)."""
+    require_device(scores.device)
+    _dev(scores, "scores", torch.float32)
+    _dev(offsets, "offsets", torch.int64)
+    n_groups = offsets.numel() - 1
+    out = torch.empty(n_groups, k, dtype=torch.int32, device=scores.device)
+    check(load().nrb_topk_order(ptr(scores), ptr(offsets), n_groups, int(k), ptr(out), stream_ptr()), "nrb_topk_order")
+    return out
+
+
 def gather_collate(table: torch.Tensor, idx: torch.Tensor, offsets: torch.Tensor, max_len: int,
                    err_flag: Optional[torch.Tensor] = None):
     """final_attention_eval_collate_fn on device (data_utils.py:784-791)."""

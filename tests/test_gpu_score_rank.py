@@ -163,3 +163,23 @@ def test_unsupported_dim_is_an_error(ops):
     with pytest.raises(NrbError):
         ops.score_rank(1, T, None, T, torch.zeros(1, dtype=torch.int32).cuda(), _csr([1]),
                        torch.zeros(1, dtype=torch.int32).cuda(), _csr([1]), 1)
+
+
+def test_topk_order_bit_exact(ops):
+    """Top-k orderings against a stable numpy argsort: ties, groups shorter than k, > 512 candidates, NaN last."""
+    rng = np.random.default_rng(9)
+    counts = np.concatenate([rng.integers(0, 60, size=200), [700, 3, 0, 1]]).astype(np.int32)
+    scores = (rng.integers(-6, 7, size=int(counts.sum())) / 4.0).astype(np.float32)  # heavy ties
+    scores[5] = np.nan
+    off = syn.csr_offsets(counts)
+    for k in (1, 5, 10, 37):
+        got = ops.topk_order(torch.from_numpy(scores).cuda(), _csr(counts), k).cpu().numpy()
+        for g in range(len(counts)):
+            s = scores[off[g]:off[g + 1]]
+            key = np.where(np.isnan(s), -np.inf, s)  # NaN last, stable among equals
+            order = np.argsort(-key, kind="stable")
+            if np.isnan(s).any():  # NaNs after every number (incl. -inf-like), by position
+                order = np.concatenate([order[~np.isnan(s[order])], order[np.isnan(s[order])]])
+            want = np.full(k, -1, dtype=np.int32)
+            want[:min(k, len(s))] = order[:k]
+            assert np.array_equal(got[g], want), (g, k)
