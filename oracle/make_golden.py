@@ -121,7 +121,6 @@ def golden_final_score(ref):
     h_off = syn.csr_offsets(imp.hist_len)
     hist_idx = np.concatenate([imp.hist_idx[h_off[i]:h_off[i + 1]] for i in range(n_imp) if hb[i]])
     hist_len = imp.hist_len[hb]
-    old_dev = dmh.DEVICE
     with torch.no_grad():
         cls = dmh.get_classification_preds(table, head)
         out = dmh.get_final_score(hist_idx, hist_len, imp.cand_idx, imp.cand_len, table, cls, pd.Series(hb), attn, wsum)
@@ -144,8 +143,6 @@ def golden_small(ref):
     # dense rank (data_utils.py:414-415) with ties, +-0 and a NaN group
     scores = np.array([0.5, 0.25, 0.5, -1.0, 0.0, -0.0, 3.0, 1e-9, 2.0, 2.0, 2.0, 1.0, np.nan, 0.3, 7.0],
                       dtype=np.float32)
-    counts = np.array([4, 4, 4, 3], dtype=np.int32)
-    counts[0], counts[1] = 4, 4  # sums to 15
     counts = np.array([4, 4, 3, 1, 3], dtype=np.int32)
     ranks = du.rank_group_preds(scores, counts)
     ranks_flat = np.concatenate([np.asarray(r, dtype=np.float64) for r in ranks])
