@@ -60,7 +60,9 @@ def parse_args():
     ap.add_argument("--workload", choices=["cfg4", "cfg5"], default="cfg4",
                     help="cfg4 = headline (replicated table); cfg5 = long-history stress, row-sharded table")
     ap.add_argument("--table-rows", type=int, default=10_000_000, help="cfg5: total table rows")
-    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p", help="cfg5: all-gather implementation")
+    ap.add_argument("--gather", choices=["p2p", "dma", "nccl", "none"], default="dma",
+                    help="cfg5: all-gather implementation (none = transform only, for diagnosis: results invalid)")
+    ap.add_argument("--chunk-rows", type=int, default=32768, help="cfg5: table rows transformed + pushed per chunk")
     return ap.parse_args()
 
 
@@ -419,6 +421,7 @@ def run_sharded(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.require_device(dev)
+    os.environ["NCCL_DEBUG"] = os.environ.get("NRB200_NCCL_DEBUG", "WARN")  # keep stdout to the JSON line
     if not dist.is_initialized():
         if world == 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -438,7 +441,8 @@ def run_sharded(args):
     local_rows = torch.nn.functional.normalize(
         torch.randn(r1 - r0, d, generator=g, device=dev, dtype=torch.float32), dim=-1).to(torch.bfloat16)
     hist_idx, h_off, cand_idx, c_off, _, _, n_h, n_c = make_device_impressions(n_imp, n_rows, h_max, 1234 + rank, dev)
-    eng = ShardedTableEngine(local_rows, n_rows, model, precision="bf16", device=dev, gather=args.gather)
+    eng = ShardedTableEngine(local_rows, n_rows, model, precision="bf16", device=dev, gather=args.gather,
+                             chunk_rows=args.chunk_rows)
     scores = torch.empty(n_c, dtype=torch.float32, device=dev)
     ranks = torch.empty(n_c, dtype=torch.int32, device=dev)
     flag = ops.new_err_flag(dev)
@@ -466,11 +470,15 @@ def run_sharded(args):
     launches0 = lib.nrb_kernel_launches()
     kev = [(ev(), ev(), ev()) for _ in range(args.steps)]
     t0, t1 = ev(), ev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     t0.record()
     for i in range(args.steps):
         step(kev[i])
     t1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     launches = lib.nrb_kernel_launches() - launches0
     ops.raise_on_index_error(flag, "bench")
     t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
@@ -488,7 +496,7 @@ def run_sharded(args):
         "config": {"workload": "long-history stress (BASELINE configs[4]): latent-attention user encoder, table "
                                "row-sharded, per-shard transform + all-gather (%s) + gather/pool/cosine/rank" % args.gather,
                    "table_rows": n_rows, "rows_per_gpu": r1 - r0, "impressions_per_gpu": n_imp, "dim": d, "latents": L,
-                   "history_max": h_max, "sum_history": n_h, "sum_candidates": n_c},
+                   "history_max": h_max, "sum_history": n_h, "sum_candidates": n_c, "chunk_rows": args.chunk_rows},
         "gpu_launches": int(launches),
         "build": {"ms": round(build_ms, 3),
                   "tflops_executed": round((r1 - r0) * f_row / (build_ms * 1e-3) / 1e12, 1),
@@ -497,6 +505,7 @@ def run_sharded(args):
         "roofline": {"bound": "hbm", "kernel": "score_rank_kernel", "achieved": round(alg_bytes / (score_ms * 1e-3) / 1e9, 1),
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(alg_bytes / (score_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                      "traffic": None, "kernel_ms": round(score_ms, 3)},
+        "clocks": clocks,
     }
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -218,6 +218,14 @@ int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride, int64_t n_
                   void* const* dst_ptrs_host, int world, int dst_dtype, int64_t dst_row_offset,
                   int64_t dst_stride, nrb_stream_t stream);
 
+/* Copy-engine variant of the same all-gather step: `n_bytes` contiguous bytes at `src` are copied to
+ * dst_ptrs_host[g] + dst_byte_offset for every g in [0, world) with one asynchronous peer copy each
+ * (a destination equal to `src` -- the chunk already sits in the local table -- is skipped).  Unlike the
+ * store kernel the DMA engines need no SM resources, so the transfer proceeds at NVLink rate even
+ * while persistent GEMM CTAs own every SM's register file.  dst_ptrs_host is a HOST array. */
+int nrb_push_bytes(const void* src, int64_t n_bytes, void* const* dst_ptrs_host, int world,
+                   int64_t dst_byte_offset, nrb_stream_t stream);
+
 /* ---- behaviour log -> CSR index builder (host; the step in front of the hot path) ------------------
  * replaces data_utils.py:168-232 split_impressions_and_history.  `impressions` / `history` are
  * '\n'-separated UTF-8 buffers with one line per behaviour row (empty history line = no history).

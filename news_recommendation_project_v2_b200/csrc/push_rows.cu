@@ -89,3 +89,18 @@ extern "C" int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride,
   NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
 }
+
+extern "C" int nrb_push_bytes(const void* src, int64_t n_bytes, void* const* dst_ptrs_host, int world,
+                              int64_t dst_byte_offset, nrb_stream_t stream) {
+  NRB_REQUIRE(src && dst_ptrs_host, "nrb_push_bytes: null pointer");
+  NRB_REQUIRE(world >= 1 && world <= kMaxPeers, "nrb_push_bytes: world must be in [1, %d]", kMaxPeers);
+  NRB_REQUIRE(n_bytes >= 0 && dst_byte_offset >= 0, "nrb_push_bytes: bad sizes");
+  if (n_bytes == 0) return NRB_OK;
+  for (int g = 0; g < world; ++g) {
+    NRB_REQUIRE(dst_ptrs_host[g] != nullptr, "nrb_push_bytes: null destination %d", g);
+    char* dst = (char*)dst_ptrs_host[g] + dst_byte_offset;
+    if ((const void*)dst == src) continue;  // already in place in the local table
+    NRB_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n_bytes, cudaMemcpyDefault, as_stream(stream)));
+  }
+  return NRB_OK;
+}

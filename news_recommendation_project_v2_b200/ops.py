@@ -302,6 +302,15 @@ def push_rows(src: torch.Tensor, dst_ptrs: list, dst_dtype: torch.dtype, dst_row
                                dtype_code(dst_dtype), dst_row_offset, dst_stride, stream_ptr()), "nrb_push_rows")
 
 
+def push_bytes(src: torch.Tensor, dst_ptrs: list, dst_byte_offset: int) -> None:
+    """Copy-engine all-gather step: the contiguous tensor `src` goes to every dst_ptrs[g] + offset (nrb_push_bytes)."""
+    require_device(src.device)
+    _dev(src, "src")
+    arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    check(load().nrb_push_bytes(ptr(src), src.numel() * src.element_size(), arr, len(dst_ptrs), dst_byte_offset,
+                                stream_ptr()), "nrb_push_bytes")
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Row-wise LayerNorm (nrb_layer_norm): x [rows, dim] fp32/bf16, gamma/beta fp32."""

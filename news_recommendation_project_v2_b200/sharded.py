@@ -8,9 +8,12 @@ all-gathered so that the bandwidth-bound gather/score/rank then runs locally on 
 shard against a full local copy.
 
 all-gather = `nrb_push_rows`: the chunk just produced is written straight into every peer's copy of the
-full table with 128-bit stores on peer-mapped symmetric memory (NVLink 5 / NVSwitch), launched on the
-compute stream right behind the chunk's GEMMs so the transfer of chunk i overlaps the transform of chunk
-i+1.  `gather="nccl"` keeps the plain `all_gather_into_tensor` variant for comparison / non-P2P setups.
+full table with 128-bit stores on peer-mapped symmetric memory (NVLink 5 / NVSwitch), launched on a
+high-priority side stream as soon as the chunk's GEMMs finish, so the transfer of chunk i overlaps the
+transform of chunk i+1 (the store-only kernel co-resides with the persistent GEMM CTAs where their
+register footprint leaves room).  `gather="dma"` = `nrb_push_bytes`: the transform writes its chunk into
+the local copy and the copy engines forward it to the peers, which needs no SM resources at all.
+`gather="nccl"` keeps the plain `all_gather_into_tensor` variant for comparison / non-P2P setups.
 """
 from __future__ import annotations
 
@@ -27,7 +30,7 @@ from .sharding import table_shard_bounds
 
 class ShardedTableEngine(ScoringEngine):
     def __init__(self, local_rows: torch.Tensor, n_rows_total: int, model: torch.nn.Module, precision=None,
-                 device: Optional[torch.device] = None, group=None, gather: str = "p2p", chunk_rows: int = 16384):
+                 device: Optional[torch.device] = None, group=None, gather: str = "dma", chunk_rows: int = 32768):
         from .latent_attention import LatentAttentionModel
 
         if not dist.is_initialized():
@@ -39,6 +42,7 @@ class ShardedTableEngine(ScoringEngine):
         self.model = model
         self.n_rows, self.dim = int(n_rows_total), int(local_rows.shape[1])
         self._streams = None
+        self._comm = None
         r0, r1 = table_shard_bounds(self.n_rows, self.world)[self.rank]
         if local_rows.shape[0] != r1 - r0:
             raise _lib.NrbError(f"rank {self.rank} must hold rows [{r0},{r1}) = {r1 - r0} rows, got {local_rows.shape[0]}")
@@ -50,7 +54,7 @@ class ShardedTableEngine(ScoringEngine):
         n, d, dev = self.n_rows, self.dim, self.device
         with torch.cuda.device(dev):
             self._names = ["cand", "hist_x"] + ([] if latent else ["hist_e"])
-            if gather == "p2p":
+            if gather in ("p2p", "dma", "none"):
                 import torch.distributed._symmetric_memory as symm_mem
 
                 self._full, self._ptrs = {}, {}
@@ -66,6 +70,12 @@ class ShardedTableEngine(ScoringEngine):
                 raise ValueError(gather)
         self.build(local_rows)
 
+    def _comm_streams(self) -> list:
+        if self._comm is None:
+            n = 1 if self.gather == "p2p" else max(1, min(self.world - 1, 2))  # >2 concurrent copies slow the GEMMs (push_bench)
+            self._comm = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(n)]
+        return self._comm
+
     def build(self, local_rows: torch.Tensor) -> None:
         """Transform this rank's shard chunk by chunk and all-gather the chunks (collective: every rank calls it)."""
         r0, r1 = self._bounds
@@ -80,22 +90,69 @@ class ShardedTableEngine(ScoringEngine):
                 fw = self.model.folded(self.dtype, dev)
             else:
                 w = _final_attention_weights(self.model, self.dtype, dev)
+            compute = torch.cuda.current_stream()
+            dma = self.gather in ("dma", "none")
+            if self.gather == "none":  # diagnosis only: peers are never written (every destination = local copy)
+                ptrs = {nm: [p[self.rank]] * self.world for nm, p in ptrs.items()}
+            comms = self._comm_streams() if ptrs is not None else []
+            row_bytes = d * torch.empty(0, dtype=self.dtype).element_size()
+
+            def after_compute():
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                for st in comms:
+                    st.wait_event(ready)
+
+            def push(nm, src, row0):
+                # "p2p": store kernel on a high-priority side stream -- it co-resides with the next chunk's persistent
+                # GEMM CTAs wherever their register footprint leaves room
+                after_compute()
+                src.record_stream(comms[0])
+                with torch.cuda.stream(comms[0]):
+                    ops.push_rows(src, ptrs[nm], self.dtype, row0, d)
+
+            def push_dma(nm, src, row0, transient=True):
+                # "dma": one peer copy per destination on the copy engines (no SM resources at all), destinations
+                # rotated by rank so that no GPU is everybody's target at the same moment
+                after_compute()
+                for k in range(self.world):
+                    g = (self.rank + 1 + k) % self.world
+                    st = comms[k % len(comms)]
+                    if transient:  # allocator-owned temporaries must outlive the copy
+                        src.record_stream(st)
+                    with torch.cuda.stream(st):
+                        ops.push_bytes(src, [ptrs[nm][g]], row0 * row_bytes)
+
             for c0 in range(0, r1 - r0, self.chunk_rows):
                 c1 = min(r1 - r0, c0 + self.chunk_rows)
                 chunk = local_rows[c0:c1].to(dev, non_blocking=True)
                 chunk = chunk.to(self.dtype).contiguous()
+                g0, g1 = r0 + c0, r0 + c1
+                if ptrs is None:
+                    full["cand"][self.rank * ns + c0:self.rank * ns + c1].copy_(chunk)
+                else:
+                    (push_dma if dma else push)("cand", chunk, g0)  # raw rows do not wait for the transform
                 if latent:
                     outs = {"hist_x": ops.latent_forward(fw, chunk.view(c1 - c0, 1, d), None,
                                                          max_tokens=LATENT_MAX_TOKENS).view(c1 - c0, d)}  # fp32
+                    if dma:  # fp32 -> table dtype into the local copy; the copy engines take it from there
+                        ops.push_rows(outs["hist_x"], [ptrs["hist_x"][self.rank]], self.dtype, g0, d)
+                elif dma:
+                    ops.final_attention_rows(chunk, w, self.dtype, x_out=full["hist_x"][g0:g1], e_out=full["hist_e"][g0:g1])
                 else:
                     x, e = ops.final_attention_rows(chunk, w, self.dtype)
                     outs = {"hist_x": x, "hist_e": e}
-                outs["cand"] = chunk
-                for nm in names:
-                    if ptrs is not None:
-                        ops.push_rows(outs[nm], ptrs[nm], self.dtype, r0 + c0, d)
-                    else:
+                for nm in names[1:]:
+                    if ptrs is None:
                         full[nm][self.rank * ns + c0:self.rank * ns + c1].copy_(outs[nm])
+                    elif dma:
+                        push_dma(nm, full[nm][g0:g1], g0, transient=False)
+                    else:
+                        push(nm, outs[nm], g0)
+            for st in comms:
+                done = torch.cuda.Event()
+                done.record(st)
+                compute.wait_event(done)
             if ptrs is None:
                 for nm in names:
                     dist.all_gather_into_tensor(full[nm], full[nm][self.rank * ns:(self.rank + 1) * ns].clone(),

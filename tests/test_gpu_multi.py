@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
         for name, model in models.items():
             ref = ScoringEngine(table, model, precision="bf16", device=dev)  # full table on every rank
             _, want_s, want_r = ref.score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len)
-            for gather in ("p2p", "nccl"):
+            for gather in ("p2p", "dma", "nccl"):
                 eng = ShardedTableEngine(table[r0:r1], n_rows, model, precision="bf16", device=dev, gather=gather,
                                          chunk_rows=6000)
                 same = torch.equal(eng.cand, ref.cand) and torch.equal(eng.hist_x, ref.hist_x)
@@ -73,4 +73,4 @@ def test_row_sharded_table_peer_store_allgather():
     assert set(res) == {0, 1}
     for rank, ok in res.items():
         assert all(ok.values()), f"rank {rank}: {ok}"
-        assert set(ok) == {"final/p2p", "final/nccl", "latent/p2p", "latent/nccl"}
+        assert set(ok) == {f"{m}/{g}" for m in ("final", "latent") for g in ("p2p", "dma", "nccl")}
