@@ -19,6 +19,17 @@
 namespace nrb {
 
 constexpr int kWarpsPerCta = 8;
+// Fused score kernel: warps per CTA.  A CTA keeps its SM slot until its slowest warp is done and impressions
+// differ widely in size (H 1..50, C 2..300), so with 8-warp CTAs ~25 % of the warp slots idled (ncu: 12.1 of 16
+// resident warps active).  One-warp CTAs hand the load balancing to the hardware CTA scheduler: same-box A/B
+// 6,175 -> 6,726 GB/s (FinalAttention pooling), 5,216 -> 5,743 GB/s (mean pooling); 2 / 4 warps land in between.
+#ifndef NRB_SCORE_WARPS
+#define NRB_SCORE_WARPS 1
+#endif
+#ifndef NRB_SCORE_GRID_MULT
+#define NRB_SCORE_GRID_MULT 4
+#endif
+constexpr int kScoreWarps = NRB_SCORE_WARPS;
 constexpr int kRankCap = 512;  // scores of one impression staged in smem (per warp)
 
 // Dense rank (descending) of s[0..n) by one warp.  r is output AND scratch: bit 31 of r[k]
@@ -77,18 +88,18 @@ __device__ __forceinline__ void load_row(const char* base, int lane, uint4 (&v)[
 }
 
 template <typename T, int NV, int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kScoreWarps * 32, 16 / kScoreWarps)
 score_rank_kernel(const ScoreRankParams p) {
   constexpr int EPV = Vec16<T>::EPV;
   constexpr int EPL = NV * EPV;  // elements owned by one lane
-  __shared__ float s_scores[kWarpsPerCta][kRankCap];
-  __shared__ int32_t s_ranks[kWarpsPerCta][kRankCap];
+  __shared__ float s_scores[kScoreWarps][kRankCap];
+  __shared__ int32_t s_ranks[kScoreWarps][kRankCap];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+  const int64_t stride = (int64_t)gridDim.x * kScoreWarps;
 
-  for (int64_t imp = (int64_t)blockIdx.x * kWarpsPerCta + warp; imp < p.n_imp; imp += stride) {
+  for (int64_t imp = (int64_t)blockIdx.x * kScoreWarps + warp; imp < p.n_imp; imp += stride) {
     const int64_t h0 = p.hist_off[imp], h1 = p.hist_off[imp + 1];
     const int64_t c0 = p.cand_off[imp], c1 = p.cand_off[imp + 1];
 
@@ -280,7 +291,7 @@ score_rank_kernel(const ScoreRankParams p) {
 
 template <typename T, int MODE>
 static int launch_score_rank_nv(int nv, const ScoreRankParams& p, int grid, cudaStream_t st) {
-  const dim3 block(kWarpsPerCta * 32);
+  const dim3 block(kScoreWarps * 32);
   switch (nv) {
 #define NRB_CASE(N)                                                  \
   case N:                                                            \
@@ -484,8 +495,8 @@ extern "C" int nrb_score_rank(int pool_mode, int dtype, int dim, int64_t n_rows,
   p.ranks = ranks;
   p.err_flag = err_flag;
   const int nv = dim * es / 512;
-  const int64_t want = (n_imp + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 64);
+  const int64_t want = (n_imp + kScoreWarps - 1) / kScoreWarps;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * (16 / kScoreWarps) * NRB_SCORE_GRID_MULT * 8);
   cudaStream_t st = as_stream(stream);
   if (dtype == NRB_F32) {
     return pool_mode == NRB_POOL_FINAL_ATTENTION

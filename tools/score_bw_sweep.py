@@ -8,7 +8,8 @@ from news_recommendation_project_v2_b200 import ops
 dev = torch.device("cuda", 0)
 d = 1024
 res = []
-for n_rows in (161_013, 1_000_000, 2_500_000, 10_000_000):
+ROWS = [int(r) for r in os.environ.get("SWEEP_ROWS", "161013,1000000,2500000,10000000").split(",")]
+for n_rows in ROWS:
     T = torch.randn(n_rows, d, device=dev, dtype=torch.bfloat16)
     X = torch.randn(n_rows, d, device=dev, dtype=torch.bfloat16)
     E = torch.rand(n_rows, d, device=dev, dtype=torch.bfloat16) + 0.5
@@ -33,6 +34,9 @@ for n_rows in (161_013, 1_000_000, 2_500_000, 10_000_000):
         r = 2 if mode == 0 else 1
         b = (r * n_h + n_c) * d * 2 + 4 * (n_h + n_c) + 8 * n_c
         res.append(dict(n_rows=n_rows, mode=mode, hmax=hmax, ms=round(ms, 3), gbs=round(b / ms / 1e6, 1)))
-        print(res[-1], flush=True)
+        print(res[-1], flush=True) if "SWEEP_QUIET" not in os.environ else None
     del T, X, E
-json.dump(res, open("gpurun_out/score_bw_sweep.json", "w"))
+if "SWEEP_QUIET" in os.environ:
+    print(" ".join("m%d/h%d=%.0f" % (r["mode"], r["hmax"], r["gbs"]) for r in res), flush=True)
+else:
+    json.dump(res, open("gpurun_out/score_bw_sweep.json", "w"))
