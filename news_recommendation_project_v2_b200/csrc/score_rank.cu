@@ -60,6 +60,29 @@ __device__ __forceinline__ void warp_dense_rank(const float* s, int32_t* r, int 
   for (int k = lane; k < n; k += 32) r[k] &= 0x7fffffff;
 }
 
+// Sums each of the N (power of two) values v[] over the 32 lanes with N-1 + log2(32/N) shuffles instead of
+// 5*N: at every halving step a lane keeps one half of its values and hands the other half to its partner.
+// Returns the total of value number (lane >> (5 - log2 N)); all lanes of that group hold identical bits.
+template <int N>
+__device__ __forceinline__ float warp_sum_transposed(float (&v)[N], int lane) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two");
+  int o = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(kFullMask, send, o);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int k = 16 / N; k > 0; k >>= 1) r += __shfl_xor_sync(kFullMask, r, k);
+  return r;
+}
+
 struct ScoreRankParams {
   const char* hist_x;
   const char* hist_e;
@@ -218,15 +241,15 @@ score_rank_kernel(const ScoreRankParams p) {
           my = 0;
         }
       }
-      float my_score = 0.f;
+      // lane l keeps the (dot, |c|^2) sums of candidate base + l; the sqrt / divide / blend then run once per lane
+      // after the block instead of once per candidate on all 32 lanes
+      float my_dot = 0.f, my_sq = 0.f;
       constexpr int CR = (16 / NV) > 0 ? (16 / NV) : 1;  // candidate rows in flight per iteration
       for (int s = 0; s < cnt; s += CR) {
         uint4 a[CR][NV];
-        int rr[CR];
 #pragma unroll
         for (int q = 0; q < CR; ++q) {
           const int r = __shfl_sync(kFullMask, my, min(s + q, cnt - 1));
-          rr[q] = r;
           load_row<T, NV>(p.cand + (int64_t)r * p.cand_stride_bytes, lane, a[q]);
         }
         __syncwarp();  // all loads issued before the first use (see the history loop)
@@ -246,25 +269,41 @@ score_rank_kernel(const ScoreRankParams p) {
             }
           }
         }
+        if constexpr ((CR & (CR - 1)) == 0) {
+          // candidate q's totals land in lanes [q*32/CR, (q+1)*32/CR); lane s+q fetches them from there
+          // (14 shuffles per 4 candidates instead of 40; the compute phase between two load batches is what the
+          // kernel's bandwidth is sensitive to: +0.7 % FinalAttention pooling, +2..5 % mean pooling, same box)
+          const float d = warp_sum_transposed<CR>(dot, lane), n2 = warp_sum_transposed<CR>(sq, lane);
+          const int src = (lane & (CR - 1)) * (32 / CR);
+          const float gd = __shfl_sync(kFullMask, d, src), gn = __shfl_sync(kFullMask, n2, src);
+          if (lane >= s && lane < s + CR) {
+            my_dot = gd;
+            my_sq = gn;
+          }
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < CR; ++q) {
+              dot[q] += __shfl_xor_sync(kFullMask, dot[q], o);
+              sq[q] += __shfl_xor_sync(kFullMask, sq[q], o);
+            }
+          }
 #pragma unroll
           for (int q = 0; q < CR; ++q) {
-            dot[q] += __shfl_xor_sync(kFullMask, dot[q], o);
-            sq[q] += __shfl_xor_sync(kFullMask, sq[q], o);
+            if (lane == s + q) {
+              my_dot = dot[q];
+              my_sq = sq[q];
+            }
           }
         }
-#pragma unroll
-        for (int q = 0; q < CR; ++q) {
-          float sc = dot[q] / fmaxf(sqrtf(sq[q]), 1e-8f);
-          if (p.cand_base != nullptr) {
-            // WeightedSumModel (modeling_utils.py:158-165) fused behind the cosine; rows without history keep
-            // the classification baseline alone (data_model_helper.py:284-299)
-            const float base = p.cand_base[rr[q]];
-            sc = (h1 > h0) ? sc * p.alpha + base * (1.0f - p.alpha) : base;
-          }
-          if (lane == s + q) my_score = sc;
-        }
+      }
+      float my_score = my_dot / fmaxf(sqrtf(my_sq), 1e-8f);
+      if (p.cand_base != nullptr && lane < cnt) {
+        // WeightedSumModel (modeling_utils.py:158-165) fused behind the cosine; rows without history keep
+        // the classification baseline alone (data_model_helper.py:284-299)
+        const float cb = p.cand_base[my];
+        my_score = (h1 > h0) ? my_score * p.alpha + cb * (1.0f - p.alpha) : cb;
       }
       if (lane < cnt) {
         p.scores[base + lane] = my_score;
