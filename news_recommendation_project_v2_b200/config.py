@@ -22,7 +22,7 @@ TORCH_DTYPE = torch.float32  # config.py:39
 #   "fp32": fp32 tables / weights, FFMA accumulation (the reference's own arithmetic; parity path)
 PRECISION = os.environ.get("NRB200_PRECISION", "bf16")
 
-# Tokens processed per latent-attention chunk (bounds the workspace: ~42 KB / token in bf16 at d=768, L=512).
+# Tokens processed per latent-attention chunk (bounds the workspace: ~23 KB / token in bf16 at d=768, L=512).
 LATENT_MAX_TOKENS = int(os.environ.get("NRB200_LATENT_MAX_TOKENS", "65536"))
 
 

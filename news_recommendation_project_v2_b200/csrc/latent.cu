@@ -173,6 +173,11 @@ struct FwdWs {
   float *logits, *h1, *h2;
   size_t bytes;
 };
+// fused softmax epilogue (logits never leave TMEM): bf16, whole 256-column tiles, a softmax row within one cluster
+static bool fused_softmax(const nrb_latent_weights* w) {
+  return w->precision == NRB_BF16 && (w->heads * w->latents_padded) % 256 == 0 && w->latents_padded <= 1024;
+}
+
 static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens, int64_t cap_items) {
   const size_t es = dtype_size(w->precision);
   const int64_t hl = (int64_t)w->heads * w->latents_padded;
@@ -183,7 +188,7 @@ static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens,
   f.m_dev = (int32_t*)ws.take(16);
   f.row_map = (int32_t*)ws.take((size_t)cap_tokens * 4);
   f.xn = ws.take((size_t)cap_tokens * w->dim * es);
-  f.logits = (float*)ws.take((size_t)cap_tokens * hl * 4);
+  f.logits = fused_softmax(w) ? nullptr : (float*)ws.take((size_t)cap_tokens * hl * 4);
   f.p = ws.take((size_t)cap_tokens * hl * es);
   f.h1 = (float*)ws.take((size_t)cap_tokens * w->dim * 4);
   f.hn = ws.take((size_t)cap_tokens * w->dim * es);
@@ -260,7 +265,7 @@ static int latent_block_rows(const nrb_latent_weights* w, const FwdWs& f, const 
                               st)) != NRB_OK)
       return rc;
     // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
-    if (P == NRB_BF16 && hl % 256 == 0 && w->latents_padded <= 1024) {
+    if (fused_softmax(w)) {
       // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
       if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
                        st, w->latents_padded, w->num_latents)) != NRB_OK)

@@ -200,3 +200,28 @@ def test_token_store_roundtrip(tmp_path):
     assert off.tolist() == [0, 7, 10, 17] and torch.equal(tokens[7:10], items[0].float())
     with pytest.raises(IndexError):
         read_token_store(db, ids=[9])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours) prints ONE JSON line with the contract keys;
+    under torchrun every rank but 0 exits without work."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--ref-sample", "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "impressions_per_sec_scored" and d["unit"] == "impressions/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
