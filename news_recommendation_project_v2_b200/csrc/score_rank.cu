@@ -198,17 +198,19 @@ score_rank_kernel(const ScoreRankParams p) {
         ss = fmaf(num[i], num[i], ss);
       }
     } else {
-      const float cntf = (float)(h1 - h0);  // 0/0 -> NaN like the reference (latent_attention.py:168)
+      // warp-uniform divisors are applied as one reciprocal + multiplies (<= 1 ulp from the division; an IEEE
+      // divide is ~12 instructions and there are 3 x 32 of them per impression here)
+      const float inv_cnt = 1.0f / (float)(h1 - h0);  // empty history: 0 * inf = NaN like the reference's 0/0 (:168)
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        num[i] = num[i] / cntf;
+        num[i] = num[i] * inv_cnt;
         ss = fmaf(num[i], num[i], ss);
       }
-      const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);  // F.normalize eps
+      const float inv_nrm = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);  // F.normalize eps
       ss = 0.f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        num[i] = num[i] / nrm;
+        num[i] = num[i] * inv_nrm;
         ss = fmaf(num[i], num[i], ss);
       }
     }
@@ -225,9 +227,9 @@ score_rank_kernel(const ScoreRankParams p) {
       }
     }
     // F.cosine_similarity: x / max(|x|, 1e-8) first (data_model_helper.py:224-227)
-    const float unorm = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
+    const float inv_unorm = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) num[i] = num[i] / unorm;
+    for (int i = 0; i < EPL; ++i) num[i] = num[i] * inv_unorm;
 
     // ---- candidates: dot + norm per row, warp-shuffle reduction -------------------------
     const int n_cand = (int)(c1 - c0);
