@@ -168,3 +168,35 @@ def test_final_score_blend_matches_reference(golden_dir):
                              alpha_param=0.7)
     np.testing.assert_allclose(out["scores"], g["scores"], atol=2e-6, rtol=0)
     assert np.array_equal(np.concatenate(oracle.rank_group_preds(g["scores"], imp.cand_len)), g["ranks"])
+
+
+def test_dense_rank_and_auc_against_the_third_party_functions():
+    """The arithmetic of the ranking / metric rows lives in un-pinned third-party code: check the
+    oracle's restatements against scipy.stats.rankdata and sklearn.roc_auc_score themselves on random groups
+    with heavy ties, +-0, infinities and NaN (data_utils.py:414-415, evaluation.py:49)."""
+    scipy_stats = pytest.importorskip("scipy.stats")
+    metrics = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(2024)
+    for trial in range(300):
+        n = int(rng.integers(1, 80))
+        kind = trial % 4
+        if kind == 0:
+            x = rng.standard_normal(n).astype(np.float32)
+        elif kind == 1:
+            x = (rng.integers(-3, 4, size=n) / 4.0).astype(np.float32)  # heavy ties, +0 / -0 below
+            x[x == 0] *= rng.choice([-1.0, 1.0], size=int((x == 0).sum())).astype(np.float32)
+        elif kind == 2:
+            x = rng.standard_normal(n).astype(np.float32)
+            x[rng.integers(0, n)] = np.inf
+            x[rng.integers(0, n)] = -np.inf
+        else:
+            x = rng.standard_normal(n).astype(np.float32)
+            x[rng.integers(0, n)] = np.nan
+        want = scipy_stats.rankdata(-x, method="dense")
+        got = oracle.dense_rank_desc(x)
+        assert np.array_equal(np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64), equal_nan=True)
+        if kind in (0, 1) and n >= 2:
+            labels = rng.integers(0, 2, size=n)
+            labels[0], labels[1] = 0, 1
+            ranks = oracle.dense_rank_desc(x)
+            assert abs(oracle._auc_tie_aware(labels, 1.0 / ranks) - metrics.roc_auc_score(labels, 1.0 / ranks)) <= 1e-12
