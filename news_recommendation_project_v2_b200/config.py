@@ -7,8 +7,23 @@ fall back to these values.
 from __future__ import annotations
 
 import os
+from enum import Enum
 
 import torch
+
+
+class NewsDataset(Enum):  # config.py:5-10 -- names of the cached tables (`<value>.pt`)
+    MINDsmall_train = "MINDsmall_train"
+    MINDsmall_dev = "MINDsmall_dev"
+    MINDlarge_train = "MINDlarge_train"
+    MINDlarge_dev = "MINDlarge_dev"
+    MINDlarge_test = "MINDlarge_test"
+
+
+class DataSubset(Enum):  # config.py:13-16
+    WITH_HISTORY = "with_history"
+    WITHOUT_HISTORY = "without_history"
+    ALL = "all"
 
 DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")  # config.py:19
 EMBEDDING_DIM = 1024  # config.py:29

@@ -83,6 +83,7 @@ def load_reference(batch_size: int = 64):
     import news_rec_utils.data_utils as data_utils
     import news_rec_utils.modeling_utils as modeling_utils
     import news_rec_utils.data_model_helper as data_model_helper
+    import news_rec_utils.components as components
 
     data_model_helper.get_attention_inference_batch_size = lambda model: 2 * batch_size
     data_model_helper.NUM_WORKERS = 0
@@ -95,6 +96,7 @@ def load_reference(batch_size: int = 64):
         data_utils=data_utils,
         modeling_utils=modeling_utils,
         data_model_helper=data_model_helper,
+        components=components,
     )
     _loaded = ns
     return ns

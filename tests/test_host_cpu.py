@@ -225,3 +225,70 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def _toy_behaviors():
+    import pandas as pd
+
+    beh = pd.DataFrame({
+        "ImpressionID": [11, 12, 13, 14],
+        # object dtype keeps the missing history as None (the reference's `if hist_row:` relies on that)
+        "History": pd.Series(["N3 N1 N3", None, "N7", "N1 N9 N2 N3"], dtype=object),
+        "Impressions": pd.Series(["N5-0 N1-1 N6-0", "N2-1 N5-0", "N8-0 N3-1 N1-0 N2-0", "N6-1 N7-0"], dtype=object),
+    })
+    news = sorted({t.split("-")[0] for r in beh["Impressions"] for t in r.split()} |
+                  {t for r in beh["History"].dropna() for t in r.split()})
+    rng = np.random.default_rng(5)
+    ctx = {
+        "behaviors": beh, "news_text_dict": {n: f"text of {n}" for n in news},
+        "news_category": {n: int(rng.integers(0, 18)) for n in news},
+        "news_subcategory": {n: int(rng.integers(0, 200)) for n in news},
+        "news_title_entity": {n: rng.standard_normal(100).astype(np.float32) for n in news},
+        "news_abstract_entity": {n: rng.standard_normal(100).astype(np.float32) for n in news},
+        "news_dataset": "toy",
+    }
+    return ctx
+
+
+def test_transform_data_and_table_components(tmp_path):
+    """The components either side of the hot path (components.py:45-114, 178-258): same context keys, dtypes and
+    row order as the reference; compared with the reference itself when it is importable here."""
+    from news_recommendation_project_v2_b200.components import (LoadEmbeddingComponent, SaveEmbeddingComponent,
+                                                                TransformData)
+    from news_recommendation_project_v2_b200.config import NewsDataset
+    from oracle import oracle
+
+    ctx = _toy_behaviors()
+    out = TransformData().transform(dict(ctx))
+    want = oracle.split_impressions_and_history(list(ctx["behaviors"]["Impressions"]), list(ctx["behaviors"]["History"]))
+    assert list(out["news_list"]) == list(want["news_list"]) and out["news_list"][0] == "N3"  # first appearance
+    for k in ("impression_rev_ind_array", "impression_len_list", "history_rev_ind_array", "history_len_list"):
+        assert np.array_equal(out[k], want[k]) and out[k].dtype == np.int32
+    assert list(out["history_bool"]) == [True, False, True, True]
+    assert out["cat_indices"].shape == (len(out["news_list"]), 1) and out["cat_indices"].dtype == torch.int32
+    assert out["title_entity_embed"].dtype == torch.float32
+    assert torch.equal(out["title_entity_embed"][0], torch.from_numpy(ctx["news_title_entity"]["N3"]))
+    assert int(out["subcat_indices"][2, 0]) == ctx["news_subcategory"][out["news_list"][2]]
+    for gone in ("behaviors", "news_category", "news_subcategory", "news_title_entity", "news_abstract_entity"):
+        assert gone not in out
+    assert "news_text_dict" in out and list(out["ImpressionID"]) == [11, 12, 13, 14]
+    with pytest.raises(AssertionError):
+        TransformData().transform({"behaviors": ctx["behaviors"]})
+
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_harness
+        ref = ref_harness.load_reference()
+        ref_out = ref.components.TransformData().transform(dict(ctx))
+        assert set(ref_out) == set(out)
+        for k, v in ref_out.items():
+            if isinstance(v, torch.Tensor):
+                assert torch.equal(v, out[k]) and v.dtype == out[k].dtype, k
+            elif isinstance(v, np.ndarray) and v.dtype != object:
+                assert np.array_equal(v, out[k]) and v.dtype == out[k].dtype, k
+
+    table = torch.randn(len(out["news_list"]), 8)
+    ctx2 = {"news_embeddings": table, "query_news_embeddings": table * 2, "news_dataset": NewsDataset.MINDsmall_dev}
+    SaveEmbeddingComponent(tmp_path / "emb").transform(ctx2)
+    assert (tmp_path / "emb" / "MINDsmall_dev.pt").exists() and (tmp_path / "emb" / "query_MINDsmall_dev.pt").exists()
+    back = LoadEmbeddingComponent(tmp_path / "emb").transform({"news_dataset": NewsDataset.MINDsmall_dev})
+    assert torch.equal(back["news_embeddings"], table) and torch.equal(back["query_news_embeddings"], table * 2)
