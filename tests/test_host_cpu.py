@@ -292,3 +292,25 @@ def test_transform_data_and_table_components(tmp_path):
     assert (tmp_path / "emb" / "MINDsmall_dev.pt").exists() and (tmp_path / "emb" / "query_MINDsmall_dev.pt").exists()
     back = LoadEmbeddingComponent(tmp_path / "emb").transform({"news_dataset": NewsDataset.MINDsmall_dev})
     assert torch.equal(back["news_embeddings"], table) and torch.equal(back["query_news_embeddings"], table * 2)
+
+
+def test_integration_stub_matches_the_abi():
+    """The reference-side ctypes stub shown in INTEGRATION.md declares the same argument lists as the library."""
+    import ctypes as C
+    import types
+
+    from news_recommendation_project_v2_b200 import _lib
+
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md.split("# news_rec_utils/_nrb200.py")[1].split("```")[0]
+    decl = [l for l in block.splitlines() if l.startswith("_lib.") and ("argtypes" in l or "restype" in l)]
+    assert len(decl) >= 5
+    fake = types.SimpleNamespace(**{n: types.SimpleNamespace() for n in _lib.PROTOTYPES})
+    env = {"C": C, "_lib": fake, "P": C.c_void_p, "I64": C.c_int64, "I32": C.c_int}
+    exec("\n".join(decl), env)
+    for name in ("nrb_final_attention_rows_workspace_bytes", "nrb_final_attention_rows", "nrb_score_rank"):
+        want = _lib.PROTOTYPES[name][1]
+        got = getattr(fake, name).argtypes
+        assert len(got) == len(want), name
+        for a, b in zip(got, want):
+            assert C.sizeof(a) == C.sizeof(b), (name, a, b)
