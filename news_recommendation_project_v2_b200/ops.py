@@ -259,7 +259,7 @@ def latent_forward(fw: FoldedLatent, x: torch.Tensor, mask: Optional[torch.Tenso
     if d != fw.dim:
         raise _lib.NrbError(f"embedding dim {d} != model dim {fw.dim}")
     lib = load()
-    max_tokens = max(int(max_tokens), S)
+    max_tokens = max(min(int(max_tokens), B * S), S)  # no larger than this call needs
     ws_bytes = lib.nrb_latent_forward_workspace_bytes(C.byref(fw.struct), max_tokens)
     ws = _workspace(dev, ws_bytes)
     if mask is not None:
@@ -339,7 +339,7 @@ def latent_forward_packed(fw: FoldedLatent, tokens: torch.Tensor, item_off: torc
     if int(off_host[-1]) != T or int(off_host[0]) != 0:
         raise _lib.NrbError("item_off must start at 0 and end at the number of tokens")
     lib = load()
-    max_tokens = max(int(max_tokens), int((off_host[1:] - off_host[:-1]).max()) if B else 1)
+    max_tokens = max(min(int(max_tokens), max(T, 1)), int((off_host[1:] - off_host[:-1]).max()) if B else 1)
     ws_bytes = lib.nrb_latent_forward_workspace_bytes(C.byref(fw.struct), max_tokens)
     ws = _workspace(dev, ws_bytes)
     out = torch.empty(B, d, dtype=torch.float32, device=dev)
