@@ -314,3 +314,22 @@ def test_integration_stub_matches_the_abi():
         assert len(got) == len(want), name
         for a, b in zip(got, want):
             assert C.sizeof(a) == C.sizeof(b), (name, a, b)
+
+
+def test_sass_contains_the_blackwell_instructions():
+    """The built sm_100a library really carries tcgen05 / TMEM / TMA code (SASS mnemonics of B200_PROFILING.md):
+    UTCHMMA(.2CTA) = tcgen05.mma (CTA pairs), LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA load / store,
+    and 128-bit global loads for the bandwidth-bound kernels."""
+    import shutil
+    import subprocess
+
+    from news_recommendation_project_v2_b200 import _lib, build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    build.build()
+    _lib.load()
+    path = os.environ.get("NRB200_LIB") or os.path.join(ROOT, "news_recommendation_project_v2_b200", "libnrb200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "LDG.E.128"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS"
