@@ -138,6 +138,26 @@ def make_device_impressions(n_imp: int, n_rows: int, h_max: int, seed: int, devi
     return hist_idx, h_off, cand_idx, c_off, hist_len.to(torch.int32), cand_len.to(torch.int32), n_h, n_c
 
 
+def make_device_labels(c_off: torch.Tensor, seed: int, device) -> torch.Tensor:
+    """int8 click labels per candidate: one uniformly placed positive per impression, the others
+    Bernoulli(0.04), at least one negative (evaluation.py:49 needs both classes)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n_imp = c_off.numel() - 1
+    cnt = c_off[1:] - c_off[:-1]
+    n_c = int(c_off[-1])
+    lab = (torch.rand(n_c, generator=g, device=device) < 0.04).to(torch.int8)
+    pos = c_off[:-1] + (torch.rand(n_imp, generator=g, device=device, dtype=torch.float64) * cnt.double()).long() \
+        .minimum(cnt - 1)
+    lab[pos] = 1
+    seg = torch.repeat_interleave(torch.arange(n_imp, device=device), cnt)
+    tot = torch.zeros(n_imp, dtype=torch.int64, device=device).index_add_(0, seg, lab.long())
+    full = torch.nonzero(tot == cnt).flatten()  # all positive: clear the slot after the forced positive
+    if full.numel():
+        nxt = c_off[:-1][full] + (pos[full] - c_off[:-1][full] + 1) % cnt[full]
+        lab[nxt] = 0
+    return lab
+
+
 def run_native(args):
     import torch.distributed as dist
 

@@ -68,6 +68,10 @@ long long nrb_kernel_launches(void);
  * a group containing a NaN gets rank 0 everywhere (host maps 0 -> NaN). */
 int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups,
                    int32_t* ranks, nrb_stream_t stream);
+/* the same for float64 scores: scipy ranks an array in its own dtype, so rank_group_preds on float64
+ * input must not merge values that differ only below fp32 resolution. */
+int nrb_dense_rank_f64(const double* scores, const int64_t* offsets, int64_t n_groups,
+                       int32_t* ranks, nrb_stream_t stream);
 
 /* ---- Stage C: per-impression top-k ordering --------------------------------------------------
  * the order evaluation.py:14,28 derives from the ranks (argsort of the scores, descending), made

@@ -624,10 +624,13 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI, OUT_BF16, CG>;
   auto kern = gemm_tc_kernel<BN, EPI, OUT_BF16, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one flag per (kernel instantiation, device)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  NRB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     NRB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int cs = CG == 2 ? 2 : (Cfg::kSoftmax ? p.cluster : 1);
   const int n_split = CG == 2 ? 1 : cs;

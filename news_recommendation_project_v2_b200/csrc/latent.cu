@@ -378,7 +378,16 @@ extern "C" int nrb_latent_forward_packed(const nrb_latent_weights* w, const void
   NRB_REQUIRE(x_dtype == NRB_F32 || x_dtype == NRB_BF16, "nrb_latent_forward_packed: bad x dtype");
   NRB_REQUIRE(n_tokens >= 0 && batch >= 0, "nrb_latent_forward_packed: bad sizes");
   NRB_REQUIRE(w->dim % 64 == 0 && w->dim <= 4096, "nrb_latent_forward_packed: unsupported dim %d", w->dim);
-  if (batch == 0 || n_tokens == 0) return NRB_OK;
+  if (batch == 0) return NRB_OK;
+  if (n_tokens == 0) {
+    // every item is empty: the reference's masked mean is 0/0 = NaN (latent_attention.py:165-168)
+    NRB_REQUIRE(item_off && pooled_out, "nrb_latent_forward_packed: null pointer");
+    const int gp0 = (int)std::min<int64_t>(batch, (int64_t)sm_count_cached() * 16);
+    pool_items_kernel<4><<<gp0, 256, 0, as_stream(stream)>>>(nullptr, w->dim, item_off, 0, batch, w->dim, pooled_out);
+    note_launch();
+    NRB_CUDA_CHECK(cudaGetLastError());
+    return NRB_OK;
+  }
   NRB_REQUIRE(x_packed && item_off && pooled_out && workspace, "nrb_latent_forward_packed: null pointer");
   FwdWs f = fwd_ws(workspace, w, n_tokens, 1);
   if (workspace_bytes < f.bytes) {

@@ -36,7 +36,8 @@ constexpr int kRankCap = 512;  // scores of one impression staged in smem (per w
 // temporarily holds "k is the first occurrence of its value".  rank_j = 1 + number of
 // distinct values greater than s_j; equal scores (incl. -0.0 == 0.0) share a rank; any NaN
 // makes the whole group rank 0 (scipy nan_policy 'propagate' -> host maps 0 to NaN).
-__device__ __forceinline__ void warp_dense_rank(const float* s, int32_t* r, int n, int lane) {
+template <typename V>
+__device__ __forceinline__ void warp_dense_rank(const V* s, int32_t* r, int n, int lane) {
   bool has_nan = false;
   for (int k = lane; k < n; k += 32) has_nan |= (s[k] != s[k]);
   if (__any_sync(kFullMask, has_nan)) {
@@ -44,14 +45,14 @@ __device__ __forceinline__ void warp_dense_rank(const float* s, int32_t* r, int 
     return;
   }
   for (int k = lane; k < n; k += 32) {
-    const float v = s[k];
+    const V v = s[k];
     int first = 1;
     for (int m = 0; m < k; ++m) first &= (s[m] != v);
     r[k] = first ? (int32_t)0x80000000 : 0;
   }
   __syncwarp();
   for (int j = lane; j < n; j += 32) {
-    const float v = s[j];
+    const V v = s[j];
     int cnt = 1;
     for (int k = 0; k < n; ++k) cnt += (int)(s[k] > v) & (int)((uint32_t)r[k] >> 31);
     r[j] = (r[j] & (int32_t)0x80000000) | cnt;
@@ -356,13 +357,16 @@ static int launch_score_rank_nv(int nv, const ScoreRankParams& p, int grid, cuda
 }
 
 // ---- standalone dense rank (rank_group_preds drop-in) ---------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-dense_rank_kernel(const float* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks) {
-  __shared__ float s_scores[kWarpsPerCta][kRankCap];
-  __shared__ int32_t s_ranks[kWarpsPerCta][kRankCap];
+// V = float (the hot path's score dtype) or double (rank_group_preds on float64 scores: scipy ranks the
+// array in its own dtype, so values that differ only below fp32 resolution must not become ties).
+template <typename V, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+dense_rank_kernel(const V* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks) {
+  __shared__ V s_scores[WARPS][kRankCap];
+  __shared__ int32_t s_ranks[WARPS][kRankCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += stride) {
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  for (int64_t g = (int64_t)blockIdx.x * WARPS + warp; g < n_groups; g += stride) {
     const int64_t c0 = offsets[g], c1 = offsets[g + 1];
     const int64_t n64 = c1 - c0;
     if (n64 <= kRankCap) {
@@ -453,16 +457,28 @@ gather_collate_kernel(const char* table, int64_t n_rows, int row_bytes, int64_t 
 
 using namespace nrb;
 
-extern "C" int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,
-                              nrb_stream_t stream) {
-  NRB_REQUIRE(n_groups >= 0, "nrb_dense_rank: n_groups < 0");
+template <typename V, int WARPS>
+static int launch_dense_rank(const V* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,
+                             nrb_stream_t stream, const char* what) {
+  NRB_REQUIRE(n_groups >= 0, "%s: n_groups < 0", what);
   if (n_groups == 0) return NRB_OK;
-  NRB_REQUIRE(scores && offsets && ranks, "nrb_dense_rank: null pointer");
-  const int64_t want = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+  NRB_REQUIRE(scores && offsets && ranks, "%s: null pointer", what);
+  const int64_t want = (n_groups + WARPS - 1) / WARPS;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
-  dense_rank_kernel<<<grid, kWarpsPerCta * 32, 0, as_stream(stream)>>>(scores, offsets, n_groups, ranks); note_launch();
+  dense_rank_kernel<V, WARPS><<<grid, WARPS * 32, 0, as_stream(stream)>>>(scores, offsets, n_groups, ranks);
+  note_launch();
   NRB_CUDA_CHECK(cudaGetLastError());
   return NRB_OK;
+}
+
+extern "C" int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,
+                              nrb_stream_t stream) {
+  return launch_dense_rank<float, kWarpsPerCta>(scores, offsets, n_groups, ranks, stream, "nrb_dense_rank");
+}
+
+extern "C" int nrb_dense_rank_f64(const double* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,
+                                  nrb_stream_t stream) {
+  return launch_dense_rank<double, 4>(scores, offsets, n_groups, ranks, stream, "nrb_dense_rank_f64");
 }
 
 extern "C" int nrb_topk_order(const float* scores, const int64_t* offsets, int64_t n_groups, int k, int32_t* out_idx,

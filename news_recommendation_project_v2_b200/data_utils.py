@@ -39,7 +39,9 @@ def ranks_to_object_array(ranks: np.ndarray, imp_counts: np.ndarray) -> np.ndarr
 def rank_group_preds(pred_scores: np.ndarray, imp_counts: np.ndarray) -> np.ndarray:
     """scipy.stats.rankdata(-x, method='dense') per impression, computed by nrb_dense_rank."""
     dev = _lib.require_device()
-    scores = np.ascontiguousarray(np.asarray(pred_scores), dtype=np.float32)
+    scores = np.asarray(pred_scores)
+    # scipy ranks the array in its own dtype (data_utils.py:415): float64 stays float64, everything else is fp32
+    scores = np.ascontiguousarray(scores, dtype=np.float64 if scores.dtype == np.float64 else np.float32)
     counts = np.asarray(imp_counts)
     off = csr_offsets(counts)
     assert off[-1] == scores.shape[0], "sum(imp_counts) must equal len(pred_scores)"

@@ -293,9 +293,17 @@ def cached_engine(news_embeddings: torch.Tensor, model: torch.nn.Module,
     key = (id(news_embeddings), news_embeddings.data_ptr(), news_embeddings._version,
            None if q is None else (id(q), q.data_ptr(), q._version), id(model), _model_fingerprint(model),
            str(precision_dtype(precision)))
-    eng = _engine_cache.get(key)
-    if eng is None:
-        _engine_cache.clear()
-        eng = ScoringEngine(news_embeddings, model, q, precision=precision)
-        _engine_cache[key] = eng
+    hit = _engine_cache.get(key)
+    if hit is not None:
+        # id / data_ptr / _version can all repeat after the table is freed (or be untouched by a numpy-side
+        # edit of a from_numpy table's storage owner): the entry is valid only for the very same live objects
+        eng, t_ref, q_ref = hit
+        if t_ref() is news_embeddings and (q is None or (q_ref is not None and q_ref() is q)):
+            return eng
+    _engine_cache.clear()
+    eng = ScoringEngine(news_embeddings, model, q, precision=precision)
+    try:
+        _engine_cache[key] = (eng, weakref.ref(news_embeddings), None if q is None else weakref.ref(q))
+    except TypeError:
+        pass
     return eng

@@ -37,13 +37,17 @@ def raise_on_index_error(flag: torch.Tensor, what: str) -> None:
 
 
 def dense_rank(scores: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
-    """int32 dense ranks (0 = NaN group).  rank_group_preds, data_utils.py:414-415."""
+    """int32 dense ranks (0 = NaN group).  rank_group_preds, data_utils.py:414-415.
+    float32 or float64 scores, ranked in their own dtype like scipy does."""
     require_device(scores.device)
-    _dev(scores, "scores", torch.float32)
+    _dev(scores, "scores")
+    if scores.dtype not in (torch.float32, torch.float64):
+        raise _lib.NrbError(f"scores must be float32 or float64, got {scores.dtype}")
     _dev(offsets, "offsets", torch.int64)
     n_groups = offsets.numel() - 1
     ranks = torch.empty(scores.numel(), dtype=torch.int32, device=scores.device)
-    check(load().nrb_dense_rank(ptr(scores), ptr(offsets), n_groups, ptr(ranks), stream_ptr()), "nrb_dense_rank")
+    fn = load().nrb_dense_rank if scores.dtype == torch.float32 else load().nrb_dense_rank_f64
+    check(fn(ptr(scores), ptr(offsets), n_groups, ptr(ranks), stream_ptr()), "nrb_dense_rank")
     return ranks
 
 
@@ -240,8 +244,10 @@ _ws_cache: dict = {}
 
 
 def _workspace(dev: torch.device, nbytes: int, tag: str = "latent") -> torch.Tensor:
-    """Grow-only per-device scratch buffer (avoids cudaMalloc in the steady state)."""
-    key = (dev.index, tag)
+    """Grow-only scratch buffer per (device, tag, stream): avoids cudaMalloc in the steady state.  Keyed by
+    the CURRENT stream as well, so that calls issued on different streams never share scratch memory (and a
+    buffer that is replaced when it grows was only ever used on the stream the allocator frees it on)."""
+    key = (dev.index, tag, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None

@@ -68,6 +68,17 @@ def make_impressions(n_imp: int, n_rows: int, h_max: int = 50, cand: str = "smal
     return Impressions(hist_idx, hist_len, cand_idx, cand_len, labels)
 
 
+def make_long_history_impressions(n_imp: int, n_rows: int, h_max: int, seed: int) -> Impressions:
+    """BASELINE configs[4] shaped impressions: the usual generator with the first impressions forced to the
+    extremes (H = h_max, 1, h_max - 1) so that the longest history the config allows is always present."""
+    imp = make_impressions(n_imp, n_rows, h_max=h_max, cand="large", seed=seed)
+    rng = np.random.default_rng(seed + 1000)
+    hist_len = imp.hist_len.copy()
+    hist_len[0], hist_len[1], hist_len[2] = h_max, 1, h_max - 1
+    hist_idx = rng.integers(0, n_rows, size=int(hist_len.sum()), dtype=np.int64).astype(np.int32)
+    return Impressions(hist_idx, hist_len, imp.cand_idx, imp.cand_len, imp.labels)
+
+
 def make_token_batch(batch: int, seq: int, dim: int, seed: int = 1234, min_len: int = 8):
     """Stage A input: x ~ randn(B,S,d) fp32, len_b ~ U[min_len, S], int32 mask."""
     g = torch.Generator().manual_seed(seed)

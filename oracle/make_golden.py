@@ -78,6 +78,32 @@ def golden_final(ref, name, dim, hidden, n_rows, n_imp, cand, seed):
     print(name, "scores", out["scores"].shape, "mean metrics", metrics.mean(axis=0))
 
 
+def golden_latent_user_encoder(ref, name, dim, L, n_rows, n_imp, h_max, seed):
+    """BASELINE configs[4] shape: LatentAttentionModel as the USER encoder (latent_attention.py:134-171) driven
+    through get_final_second_attention_score (data_model_helper.py:416-443) with histories up to h_max."""
+    model = ref_harness.make_reference_latent_model(ref, dim, L, seed=seed)
+    sd = syn.make_latent_state_dict(dim, L, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_long_history_impressions(n_imp, n_rows, h_max, seed + 3)
+    dmh = ref.data_model_helper
+    hb = pd.Series(np.ones(n_imp, dtype=bool))
+    with torch.no_grad():
+        out = dmh.get_final_second_attention_score(
+            imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, hb, model)
+        user = dmh.get_final_attention_eval(imp.hist_idx, imp.hist_len, table, model)
+    ranks = np.concatenate([np.asarray(r, dtype=np.float64) for r in out["grouped_scores"]])
+    metrics = np.array([ref.evaluation.score_row((imp.labels[i], out["grouped_scores"][i], i))
+                        for i in range(n_imp)], dtype=np.float64)
+    np.savez_compressed(
+        os.path.join(GOLD, f"{name}.npz"),
+        dim=dim, L=L, n_rows=n_rows, n_imp=n_imp, h_max=h_max, seed=seed, sd_sha256=sd_digest(sd),
+        hist_len=imp.hist_len, scores=np.asarray(out["scores"], dtype=np.float32), ranks=ranks,
+        user=user.numpy(), metrics=metrics,
+    )
+    print(name, "scores", out["scores"].shape, "max H", int(imp.hist_len.max()), "mean metrics", metrics.mean(axis=0))
+
+
 def golden_new_attention(ref):
     """NewAttention (attention.py:209-279) forward on a padded batch; weights = the reference's own seeded init
     (LayerNorm affine perturbed so it is exercised), stored because the key set is large and mostly dead."""
@@ -166,6 +192,13 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_harness.load_reference(batch_size=16)
+    only = set(sys.argv[1:])  # optional: names of the fixtures to (re)generate
+    if only:
+        if "latent_cfg5_d1024_L1024" in only:
+            golden_latent(ref, "latent_cfg5_d1024_L1024", 1024, 1024, 4, 24, seed=555)
+        if "latent_user_cfg5_d1024_L1024_H200" in only:
+            golden_latent_user_encoder(ref, "latent_user_cfg5_d1024_L1024_H200", 1024, 1024, 3000, 20, 200, seed=777)
+        return
     golden_small(ref)
     golden_new_attention(ref)
     golden_final_score(ref)
@@ -173,6 +206,9 @@ def main():
     golden_latent(ref, "latent_default_d1024_L64", 1024, 64, 4, 16, seed=4321)
     golden_final(ref, "final_small_d768", 768, 4096, 4096, 64, "small", seed=1234)
     golden_final(ref, "final_large_d1024", 1024, 4096, 2048, 48, "large", seed=99)
+    # BASELINE configs[4] shapes (d=1024, 1024 latents, histories up to 200)
+    golden_latent(ref, "latent_cfg5_d1024_L1024", 1024, 1024, 4, 24, seed=555)
+    golden_latent_user_encoder(ref, "latent_user_cfg5_d1024_L1024_H200", 1024, 1024, 3000, 20, 200, seed=777)
 
 
 if __name__ == "__main__":

@@ -207,6 +207,28 @@ def user_vectors(sd: dict, table: torch.Tensor, hist_idx: np.ndarray, hist_len: 
     return torch.cat(out)
 
 
+def latent_user_vectors(sd: dict, table: torch.Tensor, hist_idx: np.ndarray, hist_len: np.ndarray,
+                        batch: int = 16, dtype=torch.float64, heads: int = 8, dim_head: int = 512) -> torch.Tensor:
+    """get_final_attention_eval (data_model_helper.py:112-131) with LatentAttentionModel as the user encoder
+    (the slot components.py:504, 675 show): padded history gather -> latent_attention.py:134-171 per batch."""
+    groups = group_items(hist_idx, hist_len)
+    out = []
+    for s in range(0, len(groups), batch):
+        emb, msk = final_attention_eval_collate(groups[s : s + batch], table)
+        out.append(latent_pool(sd, emb, msk, heads=heads, dim_head=dim_head, dtype=dtype))
+    return torch.cat(out)
+
+
+def latent_second_attention_score(sd: dict, table: torch.Tensor, hist_idx, hist_len, cand_idx, cand_len,
+                                  dtype=torch.float64, batch: int = 16, heads: int = 8, dim_head: int = 512):
+    """get_final_second_attention_score (data_model_helper.py:416-443) with the latent-attention user encoder
+    (BASELINE configs[4])."""
+    u = latent_user_vectors(sd, table, hist_idx, hist_len, batch=batch, dtype=dtype, heads=heads, dim_head=dim_head)
+    s = cosine_scores(u, table, cand_idx, cand_len, dtype=dtype)
+    s_np = s.detach().numpy()
+    return {"user": u, "scores": s_np, "grouped_scores": rank_group_preds(s_np, cand_len)}
+
+
 # --------------------------------------------------------------------------
 # Stage C -- cosine scoring + per-impression dense rank
 # --------------------------------------------------------------------------

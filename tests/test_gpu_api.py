@@ -79,6 +79,86 @@ def test_final_second_attention_score_bf16(golden_dir):
     assert hard == 0
 
 
+@pytest.mark.parametrize("precision,tol_user,tol_score", [("fp32", 3e-6, 1e-5), ("bf16", 2e-3, 3e-3)])
+def test_latent_user_encoder_long_history_matches_reference(golden_dir, precision, tol_user, tol_score):
+    """BASELINE configs[4] shape end to end: LatentAttentionModel (d=1024, 1024 latents -> a softmax row spans a
+    4-CTA cluster in the bf16 path) as the USER encoder, histories up to 200, through the widest seam
+    (get_final_second_attention_score) against the reference's own outputs."""
+    from news_recommendation_project_v2_b200.data_model_helper import (get_final_attention_eval,
+                                                                       get_final_second_attention_score)
+    from news_recommendation_project_v2_b200.latent_attention import LatentAttentionModel
+    g = np.load(os.path.join(golden_dir, "latent_user_cfg5_d1024_L1024_H200.npz"))
+    dim, L, n_rows, n_imp, h_max, seed = (int(g[k]) for k in ("dim", "L", "n_rows", "n_imp", "h_max", "seed"))
+    model = LatentAttentionModel(dim=dim, num_latents=L, precision=precision).eval()
+    model.load_state_dict(syn.make_latent_state_dict(dim, L, seed=seed), strict=True)
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_long_history_impressions(n_imp, n_rows, h_max, seed + 3)
+    assert int(imp.hist_len.max()) == 200
+    out = get_final_second_attention_score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table,
+                                           np.ones(n_imp, dtype=bool), model, precision=precision)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=tol_score, rtol=0)
+    user = get_final_attention_eval(imp.hist_idx, imp.hist_len, table, model, precision=precision)
+    np.testing.assert_allclose(user.numpy(), g["user"], atol=tol_user, rtol=0)
+    ranks = np.concatenate([np.asarray(r) for r in out["grouped_scores"]])
+    hard, soft = _rank_mismatches(ranks, g["ranks"], g["scores"], imp.cand_len, gap=2 * tol_score)
+    assert hard == 0
+    if precision == "fp32":
+        assert soft <= 1
+        metrics = np.array([oracle.score_row(imp.labels[i], out["grouped_scores"][i]) for i in range(n_imp)])
+        np.testing.assert_allclose(metrics.mean(0), g["metrics"].mean(0), atol=5e-5, rtol=0)
+
+
+def test_checkpoint_round_trip_through_factories_and_dataloader(golden_dir, tmp_path, monkeypatch):
+    """The loader seams of the reference (modeling_utils.py:151-155, 274-279, 402-417 and the DataLoader of
+    data_model_helper.py:122-130): state_dict written with torch.save -> get_*_model(path) (strict load,
+    .to(DEVICE), eval) -> get_model_eval over a DataLoader with the reference's collate function."""
+    from functools import partial
+
+    from torch.utils.data import DataLoader
+
+    from news_recommendation_project_v2_b200 import config, modeling_utils as mu
+    from news_recommendation_project_v2_b200.data_utils import (FinalAttentionEvalDataset,
+                                                                final_attention_eval_collate_fn)
+    monkeypatch.setattr(config, "PRECISION", "fp32")
+    # ---- FinalAttention: golden user vectors of the reference's get_final_attention_eval -------------
+    g = np.load(os.path.join(golden_dir, "final_small_d768.npz"))
+    dim, hidden, n_rows, n_imp, seed = (int(g[k]) for k in ("dim", "hidden", "n_rows", "n_imp", "seed"))
+    assert hidden == 4096  # the factory's fixed hidden size (modeling_utils.py:275)
+    path = tmp_path / "Best_model_final_attention.pt"
+    torch.save(syn.make_final_attention_state_dict(dim, hidden, seed=seed), path)
+    monkeypatch.setattr(config, "REDUCED_DIM", dim)
+    model = mu.get_final_attention_model(path)
+    assert not model.training and next(model.parameters()).device.type == config.DEVICE.type == "cuda"
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand=str(g["cand"]), seed=seed + 3)
+    loader = DataLoader(FinalAttentionEvalDataset(imp.hist_idx, imp.hist_len), batch_size=24, shuffle=False,
+                        collate_fn=partial(final_attention_eval_collate_fn, news_embeddings=table), num_workers=0)
+    user = mu.get_model_eval(loader, model)
+    assert user.device.type == "cpu" and user.shape == (n_imp, dim)
+    np.testing.assert_allclose(user.numpy(), g["user"], atol=2e-5, rtol=2e-5)
+    with pytest.raises(RuntimeError):  # a checkpoint of another architecture must not load silently
+        mu.get_final_attention_model(_save(tmp_path, {"linear1.weight": torch.zeros(3, 3)}))
+    # ---- LatentAttentionModel at the reference's default dims (config.py:29-31; 64 latents) --------------
+    g = np.load(os.path.join(golden_dir, "latent_default_d1024_L64.npz"))
+    dim, L, B, S, seed = (int(g[k]) for k in ("dim", "L", "B", "S", "seed"))
+    monkeypatch.setattr(config, "REDUCED_DIM", dim)
+    monkeypatch.setattr(config, "EMBEDDING_DIM", dim)
+    path = tmp_path / "Best_model_latent.pt"
+    torch.save(syn.make_latent_state_dict(dim, L, seed=seed), path)
+    lat = mu.get_latent_attention_model(path)
+    assert sorted(lat.state_dict().keys()) == list(g["keys"])
+    x, mask = syn.make_token_batch(B, S, dim, seed=seed + 1)
+    loader = DataLoader(torch.utils.data.TensorDataset(x, mask), batch_size=3, shuffle=False)
+    pooled = mu.get_model_eval(loader, lat)  # get_model_eval calls model(*batch) positionally (:411-414)
+    np.testing.assert_allclose(pooled.numpy(), g["pooled"], atol=3e-6, rtol=0)
+
+
+def _save(tmp_path, sd):
+    p = tmp_path / "other.pt"
+    torch.save(sd, p)
+    return p
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
 def test_final_attention_module_forward(precision, tol):
     """FinalAttention.forward on a padded, masked batch (the DataLoader path of the reference)."""

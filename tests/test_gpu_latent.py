@@ -26,7 +26,7 @@ def _model(dim, L, seed, precision, **kw):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["latent_cfg1_d768_L512", "latent_default_d1024_L64"])
+@pytest.mark.parametrize("name", ["latent_cfg1_d768_L512", "latent_default_d1024_L64", "latent_cfg5_d1024_L1024"])
 def test_latent_pool_matches_reference_golden(golden_dir, name, precision):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     dim, L, B, S, seed = (int(g[k]) for k in ("dim", "L", "B", "S", "seed"))
@@ -155,3 +155,21 @@ def test_apply_token_attn_from_token_store(tmp_path):
     want = oracle.latent_pool(m.state_dict(), x, mask, heads=4, dim_head=64).float()
     # bf16 token storage in read_token_store (default) vs fp16 source: compare at bf16 input precision
     np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-3, rtol=0)
+
+
+def test_packed_all_empty_items_give_nan():
+    """A chunk whose items are all empty returns NaN rows like the reference's 0/0 masked mean, never
+    uninitialised memory."""
+    from news_recommendation_project_v2_b200.latent_attention import LatentAttentionModel
+    m = LatentAttentionModel(dim=256, num_latents=64, heads=4, dim_head=64, precision="bf16").eval()
+    m.load_state_dict(syn.make_latent_state_dict(256, 64, heads=4, dim_head=64, seed=1))
+    out = m.forward_packed(torch.zeros(0, 256, device="cuda"), torch.zeros(4, dtype=torch.int64))
+    assert out.shape == (3, 256) and torch.isnan(out).all()
+    # mixed: empty items between real ones
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randn(10, 256, generator=g)
+    off = torch.tensor([0, 0, 4, 4, 10, 10])
+    out = m.forward_packed(tok.cuda(), off).cpu()
+    assert torch.isnan(out[[0, 2, 4]]).all() and torch.isfinite(out[[1, 3]]).all()
+    want = m.forward_packed(tok.cuda(), torch.tensor([0, 4, 10])).cpu()
+    assert torch.equal(out[[1, 3]], want)

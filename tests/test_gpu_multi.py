@@ -74,3 +74,22 @@ def test_row_sharded_table_peer_store_allgather():
     for rank, ok in res.items():
         assert all(ok.values()), f"rank {rank}: {ok}"
         assert set(ok) == {f"{m}/{g}" for m in ("final", "latent") for g in ("p2p", "dma", "nccl")}
+
+
+def test_tcgen05_gemm_on_second_device_same_process():
+    """cudaFuncSetAttribute is per device: the first tcgen05 GEMM on cuda:1 in a process that already ran
+    one on cuda:0 must still get its ~200 KB of dynamic shared memory."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from news_recommendation_project_v2_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(300, 256, generator=g).to(torch.bfloat16)
+    w = (torch.randn(512, 256, generator=g) / 16).to(torch.bfloat16)
+    want = a.double() @ w.double().T
+    for d in (0, 1, 0, 1):
+        with torch.cuda.device(d):
+            y = ops.linear(a.cuda(d), w.cuda(d), None, 0, None, torch.float32)
+            p = ops.linear(a.cuda(d), w.cuda(d), None, 5, None, torch.bfloat16, group=512, group_valid=512)
+            torch.cuda.synchronize(d)
+        torch.testing.assert_close(y.cpu().double(), want, atol=2e-4, rtol=2e-4)
+        assert abs(float(p.float().sum(-1).mean()) - 1.0) < 1e-2

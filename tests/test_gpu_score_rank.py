@@ -183,3 +183,41 @@ def test_topk_order_bit_exact(ops):
             want = np.full(k, -1, dtype=np.int32)
             want[:min(k, len(s))] = order[:k]
             assert np.array_equal(got[g], want), (g, k)
+
+
+def test_rank_group_preds_float64_not_merged_below_fp32(ops):
+    """scipy ranks float64 scores in float64 (data_utils.py:415): values closer than fp32 resolution stay distinct."""
+    from news_recommendation_project_v2_b200.data_utils import rank_group_preds
+    scores = np.array([0.5, 0.5 + 1e-12, 0.5 - 1e-12, 0.25, 1.0, 1.0 + 1e-13, 1.0, np.nan, 2.0], dtype=np.float64)
+    counts = np.array([4, 3, 2], dtype=np.int32)
+    got = rank_group_preds(scores, counts)
+    want = oracle.rank_group_preds(scores, counts)
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g, dtype=np.float64), np.asarray(w, dtype=np.float64), equal_nan=True)
+    # the same bits rounded to fp32 DO tie (and the fp32 entry point says so)
+    got32 = rank_group_preds(scores.astype(np.float32), counts)
+    assert np.array_equal(np.asarray(got32[0]), np.array([1, 1, 1, 2], dtype=np.float32))
+    rng = np.random.default_rng(5)
+    counts = np.concatenate([rng.integers(1, 90, size=200), [600]]).astype(np.int32)
+    scores = rng.standard_normal(int(counts.sum()))
+    scores[::7] = scores[1::7][: len(scores[::7])]  # ties
+    got = np.concatenate([np.asarray(r) for r in rank_group_preds(scores, counts)])
+    want = np.concatenate([np.asarray(r) for r in oracle.rank_group_preds(scores, counts)])
+    assert np.array_equal(got, want)
+
+
+def test_cached_engine_never_returns_a_stale_table(ops):
+    """The engine cache is valid only for the very same live table object."""
+    from news_recommendation_project_v2_b200 import engine
+    from news_recommendation_project_v2_b200.modeling_utils import FinalAttention
+    model = FinalAttention(256, 512, precision="fp32").eval()
+    model.load_state_dict(syn.make_final_attention_state_dict(256, 512, seed=3))
+    t1 = syn.make_table(300, 256, seed=1)
+    e1 = engine.cached_engine(t1, model, precision="fp32")
+    assert engine.cached_engine(t1, model, precision="fp32") is e1
+    key = next(iter(engine._engine_cache))
+    t2 = syn.make_table(300, 256, seed=2)
+    # forge the situation the advisor described: same key, different (new) table object
+    engine._engine_cache[key] = (e1, __import__("weakref").ref(t2), None)
+    e2 = engine.cached_engine(t1, model, precision="fp32")
+    assert e2 is not e1

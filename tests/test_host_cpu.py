@@ -72,6 +72,36 @@ def test_state_dict_keys_match_reference(golden_dir):
         [f"linear{i}.weight" for i in range(1, 6)] + [f"linear{i}.bias" for i in range(1, 5)])
 
 
+def test_reference_checkpoints_load_through_the_factories(tmp_path, monkeypatch):
+    """torch.save(reference_module.state_dict()) -> get_*_model(path) (modeling_utils.py:151-155, 274-279): strict
+    load, every tensor identical, eval mode.  Needs the reference tree (this container); loading needs no GPU."""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from news_recommendation_project_v2_b200 import config, modeling_utils as mu
+    ref = ref_harness.load_reference()
+    monkeypatch.setattr(config, "DEVICE", torch.device("cpu"))
+    for dim in (256, 1024):
+        monkeypatch.setattr(config, "REDUCED_DIM", dim)
+        monkeypatch.setattr(config, "EMBEDDING_DIM", dim)
+        ref_fa = ref_harness.make_reference_final_attention(ref, dim, 4096, seed=dim)
+        p = tmp_path / f"fa_{dim}.pt"
+        torch.save(ref_fa.state_dict(), p)
+        ours = mu.get_final_attention_model(p)
+        assert not ours.training
+        for k, v in ref_fa.state_dict().items():
+            assert torch.equal(ours.state_dict()[k], v), k
+        ref_lat = ref_harness.make_reference_latent_model(ref, dim, 64, seed=dim + 1)
+        p = tmp_path / f"lat_{dim}.pt"
+        torch.save(ref_lat.state_dict(), p)
+        ours = mu.get_latent_attention_model(p)
+        assert not ours.training and set(ours.state_dict()) == set(ref_lat.state_dict())
+        for k, v in ref_lat.state_dict().items():
+            assert torch.equal(ours.state_dict()[k], v), k
+    with pytest.raises(RuntimeError):
+        mu.get_latent_attention_model(tmp_path / "fa_1024.pt")  # wrong architecture: strict load refuses
+
+
 def test_group_items_pad_and_rank_object_arrays():
     from news_recommendation_project_v2_b200.data_utils import group_items, pad_to_maxlen, ranks_to_object_array
     items = np.arange(10, dtype=np.int32)

@@ -23,7 +23,7 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
 
 
-@pytest.mark.parametrize("name", ["latent_cfg1_d768_L512", "latent_default_d1024_L64"])
+@pytest.mark.parametrize("name", ["latent_cfg1_d768_L512", "latent_default_d1024_L64", "latent_cfg5_d1024_L1024"])
 def test_latent_pool_matches_reference(golden_dir, name):
     g = _load(golden_dir, name)
     dim, L, B, S, seed = (int(g[k]) for k in ("dim", "L", "B", "S", "seed"))
@@ -76,6 +76,26 @@ def test_final_attention_score_rank_matches_reference(golden_dir, name):
     assert np.array_equal(ranks_from_ref_scores, ref_ranks)
     # metrics from the reference's ranks
     grouped = oracle.group_items(ref_ranks, imp.cand_len)
+    m = np.array([oracle.score_row(imp.labels[i], grouped[i]) for i in range(n_imp)])
+    np.testing.assert_allclose(m, g["metrics"], atol=1e-12, rtol=0)
+
+
+def test_latent_user_encoder_long_history_matches_reference(golden_dir):
+    """BASELINE configs[4] shape (d=1024, 1024 latents, histories up to 200) through
+    get_final_second_attention_score with LatentAttentionModel as the user encoder."""
+    g = _load(golden_dir, "latent_user_cfg5_d1024_L1024_H200")
+    dim, L, n_rows, n_imp, h_max, seed = (int(g[k]) for k in ("dim", "L", "n_rows", "n_imp", "h_max", "seed"))
+    sd = syn.make_latent_state_dict(dim, L, seed=seed)
+    assert _digest(sd) == str(g["sd_sha256"])
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_long_history_impressions(n_imp, n_rows, h_max, seed + 3)
+    assert np.array_equal(imp.hist_len, g["hist_len"]) and int(imp.hist_len.max()) == h_max == 200
+    out = oracle.latent_second_attention_score(sd, table, imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len,
+                                               dtype=torch.float64, batch=5)
+    np.testing.assert_allclose(out["user"].float().numpy(), g["user"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=2e-6, rtol=0)
+    assert np.array_equal(np.concatenate(oracle.rank_group_preds(g["scores"], imp.cand_len)), g["ranks"])
+    grouped = oracle.group_items(g["ranks"], imp.cand_len)
     m = np.array([oracle.score_row(imp.labels[i], grouped[i]) for i in range(n_imp)])
     np.testing.assert_allclose(m, g["metrics"], atol=1e-12, rtol=0)
 
