@@ -132,6 +132,12 @@ int nrb_linear(int precision, int epilogue, int out_dtype,
                const float* res, int64_t ldres, void* y, int64_t ldy,
                int64_t M, int N, int K, int group, int group_valid, nrb_stream_t stream);
 
+/* dst[r, :] = (dst_dtype) src[r, :] for a [n_rows, dim] row block (strides in elements): the fp32 -> bf16 rounding
+ * (round to nearest even, = torch .to(bfloat16)) of the cached table `embeddings/<dataset>.pt`
+ * (components.py:199-214 writes fp32) on its way into HBM, and the fp32 view of bf16 rows. */
+int nrb_convert_rows(const void* src, int src_dtype, int64_t src_stride, void* dst, int dst_dtype,
+                     int64_t dst_stride, int64_t n_rows, int dim, nrb_stream_t stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dimension (biased variance, eps inside the sqrt):
  * torch.nn.LayerNorm at latent_attention.py:10-19 (eps 1e-5) and attention.py:170-171,193 (eps 1e-12). */
 int nrb_layer_norm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "nrb_score_rank": (_i32, [_i32, _i32, _i32, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _i64, _c_void_p, _f32,
                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64,
                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "nrb_convert_rows": (_i32, [_c_void_p, _i32, _i64, _c_void_p, _i32, _i64, _i64, _i32, _c_void_p]),
     "nrb_layer_norm": (_i32, [_c_void_p, _i32, _i64, _c_void_p, _c_void_p, _f32, _c_void_p, _i32, _i64, _i64, _i32,
                               _c_void_p]),
     "nrb_linear": (_i32, [_i32, _i32, _i32, _c_void_p, _i64, _c_void_p, _i64, _c_void_p, _c_void_p, _i64,

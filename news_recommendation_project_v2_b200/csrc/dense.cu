@@ -212,9 +212,36 @@ convert_rows_kernel(const void* src, int src_dtype, int64_t lds, void* dst, int 
   }
 }
 
+// fp32 -> bf16, 8 elements per thread: two 128-bit loads, one 128-bit store (the host-table upload path)
+__global__ void __launch_bounds__(256)
+convert_f32_bf16_vec_kernel(const float* src, int64_t lds, __nv_bfloat16* dst, int64_t ldd, int64_t rows, int cols8) {
+  const int64_t total = rows * cols8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols8;
+    const int c = (int)(i - r * cols8) * 8;
+    const uint4 a = ldg_stream_128(src + r * lds + c), b = ldg_stream_128(src + r * lds + c + 4);
+    uint4 o;
+    o.x = pack_bf16x2(__uint_as_float(a.x), __uint_as_float(a.y));
+    o.y = pack_bf16x2(__uint_as_float(a.z), __uint_as_float(a.w));
+    o.z = pack_bf16x2(__uint_as_float(b.x), __uint_as_float(b.y));
+    o.w = pack_bf16x2(__uint_as_float(b.z), __uint_as_float(b.w));
+    *reinterpret_cast<uint4*>(dst + r * ldd + c) = o;
+  }
+}
+
 int convert_rows(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows,
                  int cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return NRB_OK;
+  if (src_dtype == NRB_F32 && dst_dtype == NRB_BF16 && cols % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t want8 = (rows * (cols / 8) + 255) / 256;
+    const int grid8 = (int)std::min<int64_t>(want8, (int64_t)sm_count_cached() * 16);
+    convert_f32_bf16_vec_kernel<<<grid8, 256, 0, st>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows,
+                                                       cols / 8);
+    note_launch();
+    NRB_CUDA_CHECK(cudaGetLastError());
+    return NRB_OK;
+  }
   const int64_t want = (rows * cols + 255) / 256;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 32);
   convert_rows_kernel<<<grid, 256, 0, st>>>(src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols); note_launch();
@@ -281,6 +308,16 @@ constexpr int64_t kFaChunkRows = 16384;
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_convert_rows(const void* src, int src_dtype, int64_t src_stride, void* dst, int dst_dtype,
+                                int64_t dst_stride, int64_t n_rows, int dim, nrb_stream_t stream) {
+  NRB_REQUIRE((src_dtype == NRB_F32 || src_dtype == NRB_BF16) && (dst_dtype == NRB_F32 || dst_dtype == NRB_BF16),
+              "nrb_convert_rows: bad dtype");
+  NRB_REQUIRE(n_rows >= 0 && dim > 0, "nrb_convert_rows: bad sizes");
+  if (n_rows == 0) return NRB_OK;
+  NRB_REQUIRE(src && dst, "nrb_convert_rows: null pointer");
+  return convert_rows(src, src_dtype, src_stride, dst, dst_dtype, dst_stride, n_rows, dim, as_stream(stream));
+}
 
 extern "C" int nrb_layer_norm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
                               void* y, int y_dtype, int64_t ldy, int64_t rows, int dim, nrb_stream_t stream) {

@@ -36,10 +36,13 @@ def resident_table(table: torch.Tensor, dtype: torch.dtype, device: torch.device
     if hit is not None and hit[0]() is table:
         return hit[1]
     # copy in the source dtype first (a pinned table then crosses PCIe by DMA) and convert on the GPU
-    dev_t = table.detach().to(device=device, non_blocking=True)
+    dev_t = table.detach().to(device=device, non_blocking=True).contiguous()
     if dev_t.dtype != dtype:
-        dev_t = dev_t.to(dtype)
-    dev_t = dev_t.contiguous()
+        if dev_t.dtype in (torch.float32, torch.bfloat16) and dev_t.dim() == 2:
+            with torch.cuda.device(device):
+                dev_t = ops.convert_rows(dev_t, dtype)  # native rounding kernel, not an ATen copy
+        else:
+            dev_t = dev_t.to(dtype)
     if len(_table_cache) > 8:
         _table_cache.clear()
     try:
@@ -140,7 +143,7 @@ class ScoringEngine:
                 ev.record(s_in)
             cur.wait_event(ev)
             if not direct:
-                self.cand[r0:r1].copy_(stage[b][: r1 - r0])  # fp32 -> bf16 on the device
+                ops.convert_rows(stage[b][: r1 - r0], self.dtype, out=self.cand[r0:r1])  # fp32 -> bf16 on the device
                 free_ev[b] = torch.cuda.Event()
                 free_ev[b].record(cur)
             ops.final_attention_rows(self.cand[r0:r1], self._fa_weights, self.dtype, x_out=self.hist_x[r0:r1],

@@ -317,6 +317,21 @@ def push_bytes(src: torch.Tensor, dst_ptrs: list, dst_byte_offset: int) -> None:
                                 stream_ptr()), "nrb_push_bytes")
 
 
+def convert_rows(src: torch.Tensor, out_dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[rows, dim] fp32 <-> bf16 on the device (nrb_convert_rows): the table's way into HBM, no ATen copy kernel."""
+    dev = require_device(src.device)
+    if not src.is_cuda or src.dim() != 2 or src.stride(1) != 1:
+        raise _lib.NrbError("src must be a CUDA [rows, dim] tensor with unit inner stride")
+    rows, dim = src.shape
+    if out is None:
+        out = torch.empty(rows, dim, dtype=out_dtype, device=dev)
+    if out.dtype != out_dtype or tuple(out.shape) != (rows, dim) or out.stride(1) != 1 or not out.is_cuda:
+        raise _lib.NrbError("out must be a CUDA [rows, dim] tensor of the requested dtype")
+    check(load().nrb_convert_rows(ptr(src), dtype_code(src.dtype), src.stride(0), ptr(out), dtype_code(out_dtype),
+                                  out.stride(0), rows, dim, stream_ptr()), "nrb_convert_rows")
+    return out
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Row-wise LayerNorm (nrb_layer_norm): x [rows, dim] fp32/bf16, gamma/beta fp32."""

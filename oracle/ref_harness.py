@@ -20,18 +20,39 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("NRB_REFERENCE_SRC", "/root/reference/src")
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/build_ref.py
+
+
+def _reference_src() -> str:
+    """The reference tree itself in the build container; on the GPU box the unmodified copy that
+    oracle/build_ref.py pip-installed into oracle/_ref (git-ignored, travels with gpurun)."""
+    env = os.environ.get("NRB_REFERENCE_SRC")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/news_rec_utils"):
+        return "/root/reference/src"
+    return _INSTALLED
+
+
+REFERENCE_SRC = _reference_src()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_SRC, "news_rec_utils"))
 
 
+def reference_origin() -> str:
+    return "oracle/_ref (pip-installed unmodified reference)" if REFERENCE_SRC == _INSTALLED else REFERENCE_SRC
+
+
 _loaded = None
 
 
-def load_reference(batch_size: int = 64):
-    """Import the reference package; returns a namespace of its modules."""
+def load_reference(batch_size: int = 64, device: str | None = None):
+    """Import the reference package; returns a namespace of its modules.
+
+    `device`: "cpu" / "cuda" overrides the reference's DEVICE constant (config.py:19 picks cuda when it is
+    available) in every module that imported it -- a run-time placement choice, no arithmetic."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -87,6 +108,13 @@ def load_reference(batch_size: int = 64):
 
     data_model_helper.get_attention_inference_batch_size = lambda model: 2 * batch_size
     data_model_helper.NUM_WORKERS = 0
+    if device is not None:
+        import torch
+
+        dev = torch.device(device)
+        for mod in (config, data_utils, modeling_utils, data_model_helper, components):
+            if hasattr(mod, "DEVICE"):
+                mod.DEVICE = dev
 
     ns = types.SimpleNamespace(
         config=config,
