@@ -49,7 +49,7 @@ extern "C" {
 #define NRB_EPI_RELU 1      /* y = relu(acc + bias)                   modeling_utils.py:218-221 */
 #define NRB_EPI_EXP 2       /* y = exp(acc + bias)                    modeling_utils.py:224     */
 #define NRB_EPI_RESIDUAL 3  /* y = acc + bias + res                   latent_attention.py:162-163 */
-#define NRB_EPI_GEGLU 4     /* y[j] = a_j * gelu_erf(g_j), W rows interleaved (a0,g0,a1,g1..) latent_attention.py:24-27 */
+#define NRB_EPI_GEGLU 4     /* y[j] = a_j * gelu_erf(g_j), W rows interleaved in pairs (a0,a1,g0,g1,a2,a3,g2,g3..) latent_attention.py:24-27 */
 #define NRB_EPI_SOFTMAX 5   /* y = softmax over each group of `group` columns (first `group_valid` valid); latent_attention.py:69-72 */
 
 typedef void* nrb_stream_t;
@@ -187,7 +187,7 @@ typedef struct nrb_latent_weights {
   const float* ln1_b;
   const float* ln2_w;   /* cross_attend_blocks.1.norm                                 */
   const float* ln2_b;
-  const void* w_ff1;    /* [8*dim, dim] rows interleaved (a0,g0,a1,g1,...)            */
+  const void* w_ff1;    /* [8*dim, dim] rows interleaved in pairs (a0,a1,g0,g1,...)    */
   const float* b_ff1;   /* [8*dim] interleaved the same way                           */
   const void* w_ff2;    /* [dim, 4*dim]                                               */
   const float* b_ff2;   /* [dim]                                                      */

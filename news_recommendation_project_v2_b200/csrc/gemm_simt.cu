@@ -150,8 +150,9 @@ gemm_simt_kernel(const SimtParams p) {
         }
       }
       if (EPI == NRB_EPI_GEGLU) {
-        const float o0 = v[0] * gelu_erf_f32(v[1]);
-        const float o1 = v[2] * gelu_erf_f32(v[3]);
+        // W rows interleaved in pairs (a0,a1,g0,g1,...): same layout as the tensor-core kernel
+        const float o0 = v[0] * gelu_erf_f32(v[2]);
+        const float o1 = v[1] * gelu_erf_f32(v[3]);
         const int oc = col >> 1;
         if (OUT_BF16) {
           *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + oc) = pack_bf16x2(o0, o1);

@@ -47,13 +47,18 @@ struct GemmCfg {
   static_assert(CG == 1 || (CG == 2 && BN == 256 && EPI != NRB_EPI_SOFTMAX), "CTA pairs: 256-wide tiles, no softmax");
   static constexpr bool kStaged = OUT_BF16;
   static constexpr bool kSoftmax = EPI == NRB_EPI_SOFTMAX;
+  // fp32 outputs: every epilogue warp transposes its 32x32 accumulator chunk through a private 4 KB smem patch so
+  // that the residual loads and the output stores touch 4 rows x 128 contiguous bytes per instruction instead of
+  // 32 rows x 16 bytes (GEGLU with fp32 output -- unused on the hot path -- keeps the direct row-per-lane stores)
+  static constexpr bool kXpose = !OUT_BF16 && EPI != NRB_EPI_GEGLU;
+  static constexpr int kXposeBytes = kXpose ? kEpiWarps * 4096 : 0;
   static constexpr int kHalves = BN / 128;  // epilogue column halves (128 accumulator columns each)
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;  // a CTA pair splits the N rows of W between its two CTAs
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kStaged ? kHalves * 2 * kGroupBytes : 0;  // double buffered per half
   static constexpr int kXchgBytes = kSoftmax ? 2 * 2 * (2 * kMaxCluster) * 128 * 4 : 0;  // [parity][m|s][participant][row]
-  static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXchgBytes;
+  static constexpr int kFixedBytes = 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes + kXposeBytes + kXchgBytes;
   static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
 #ifndef NRB_MAX_STAGES
 #define NRB_MAX_STAGES 6
@@ -93,6 +98,36 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 constexpr float kLog2e = 1.4426950408889634f;
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per lane per instruction) ----
+// The fused epilogues are bound by the FMA pipe (a 3-register FFMA issues every other cycle per SM sub-partition);
+// the packed forms halve the instruction count of the polynomial / scaling work.  A pair lives in one 64-bit
+// register; tcgen05.ld hands out consecutive registers, so neighbouring accumulator columns pack for free.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // erf-GELU (F.gelu default, latent_attention.py:27): g * Phi(g) with Phi from the Abramowitz-Stegun 7.1.26
 // erfc approximation (|abs err| <= 1.5e-7, far below the bf16 rounding of the output); the negative branch
 // uses erfc directly so that there is no cancellation.
@@ -107,22 +142,43 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
   // g * Phi(g) = relu(g) - |g| * half_erfc  (g >= 0: g(1-h); g < 0: g*h) -- no select, no cancellation
   return fmaf(-fabsf(g), half_erfc, fmaxf(g, 0.f));
 }
+// the same for two gates at once: a2 * gelu(g2), 12 packed FMA-pipe instructions + 4 MUFU per pair of outputs
+__device__ __forceinline__ f32x2 geglu2(f32x2 a2, f32x2 g2) {
+  float g0, g1;
+  unpack2(g2, g0, g1);
+  const f32x2 ag = pack2(fabsf(g0), fabsf(g1));
+  const f32x2 z = mul2(ag, splat2(0.70710678118654752440f));
+  float d0, d1;
+  unpack2(fma2(splat2(0.3275911f), z, splat2(1.0f)), d0, d1);
+  const f32x2 t = pack2(rcp_approx(d0), rcp_approx(d1));
+  // coefficients carry -0.5: p = -0.5 * poly(t), so that the last step is one fused multiply-add
+  f32x2 p = fma2(t, splat2(-0.5f * 1.061405429f), splat2(-0.5f * -1.453152027f));
+  p = fma2(p, t, splat2(-0.5f * 1.421413741f));
+  p = fma2(p, t, splat2(-0.5f * -0.284496736f));
+  p = fma2(p, t, splat2(-0.5f * 0.254829592f));
+  float e0, e1;
+  unpack2(mul2(z, mul2(z, splat2(-kLog2e))), e0, e1);
+  const f32x2 ex = pack2(ex2_approx(e0), ex2_approx(e1));
+  const f32x2 neg_half_erfc = mul2(mul2(p, t), ex);  // -0.5 * erfc(|z|)
+  const f32x2 gelu = fma2(ag, neg_half_erfc, pack2(fmaxf(g0, 0.f), fmaxf(g1, 0.f)));
+  return mul2(a2, gelu);
+}
 
 // ---- shared epilogue math: 32 accumulator columns of one row -> post-activation fp32 values -------------
 template <int EPI>
 __device__ __forceinline__ void activate_chunk(const uint32_t (&acc)[32], const GemmParams& p, int64_t row,
                                                int col0, bool row_ok, float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-      v[j] += b.x;
-      v[j + 1] += b.y;
-      v[j + 2] += b.z;
-      v[j + 3] += b.w;
+      unpack2(add2(pack2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])), pack2(b.x, b.y)), v[j], v[j + 1]);
+      unpack2(add2(pack2(__uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])), pack2(b.z, b.w)), v[j + 2],
+              v[j + 3]);
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   }
   if (EPI == NRB_EPI_RELU) {
 #pragma unroll
@@ -156,9 +212,11 @@ __device__ __forceinline__ void activate_chunk(const uint32_t (&acc)[32], const 
       }
     }
   } else if (EPI == NRB_EPI_GEGLU) {
-    // W rows interleaved (a0,g0,a1,g1,...): 32 accumulator columns -> 16 outputs in v[0..15]
+    // W rows interleaved in pairs (a0,a1,g0,g1,a2,a3,g2,g3,...): neighbouring accumulator columns hold two values
+    // or two gates, i.e. one packed operand each; 32 accumulator columns -> 16 outputs in v[0..15]
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_fast(v[2 * j + 1]);
+    for (int q = 0; q < 8; ++q)
+      unpack2(geglu2(pack2(v[4 * q], v[4 * q + 1]), pack2(v[4 * q + 2], v[4 * q + 3])), v[2 * q], v[2 * q + 1]);
   }
 }
 
@@ -193,8 +251,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // [kHalves][2][16 KB], 1024-aligned
-  float* xbuf = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][2*kMaxCluster][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kXchgBytes);
+  uint8_t* xpose = staging + Cfg::kStagingBytes;                         // [kEpiWarps][4 KB]
+  float* xbuf = reinterpret_cast<float*>(xpose + Cfg::kXposeBytes);      // [2][2*kMaxCluster][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xpose + Cfg::kXposeBytes + Cfg::kXchgBytes);
   uint64_t* full_bar = bars;                      // [kStages] TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages] MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;       // [2] MMA -> epilogue
@@ -393,14 +452,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], xv[j]);
           const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           const float mb = (m == -INFINITY ? 0.f : m) * kLog2e;  // an all-masked chunk contributes nothing
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          f32x2 s2[2] = {splat2(0.f), splat2(0.f)};  // 4 independent chains, two per packed register
+          const f32x2 l2e = splat2(kLog2e), nmb = splat2(-mb);
           uint32_t ev[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = ex2_approx(fmaf(xv[j], kLog2e, -mb));
-            s4[j & 3] += e;
-            ev[j] = __float_as_uint(e);
+          for (int j = 0; j < 32; j += 2) {
+            float a0, a1;
+            unpack2(fma2(pack2(xv[j], xv[j + 1]), l2e, nmb), a0, a1);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            s2[(j >> 1) & 1] = add2(s2[(j >> 1) & 1], pack2(e0, e1));
+            ev[j] = __float_as_uint(e0);
+            ev[j + 1] = __float_as_uint(e1);
           }
+          float s4[4];
+          unpack2(s2[0], s4[0], s4[1]);
+          unpack2(s2[1], s4[2], s4[3]);
           // exp(x - m_c) replaces the logit IN TMEM: pass B only rescales, so each element costs one ex2
           ptx::tmem_st_32x32(taddr + (uint32_t)(c * 32), ev);
           mx[c] = m;
@@ -467,8 +533,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // p = exp(x - m_c) * 2^((m_c - M) log2e) / S   (masked columns already hold exp(-inf) = 0)
           const float f = ex2_approx(mcb[c] - mx[c] * kLog2e) / sm[c];
           float v[32];
+          const f32x2 f2 = splat2(f);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * f;
+          for (int j = 0; j < 32; j += 2)
+            unpack2(mul2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), f2), v[j], v[j + 1]);
           if ((c & 1) == 0) {  // first chunk of a group: the buffer used two groups ago must be drained
             if (issuer) ptx::tma_store_wait_read1();
             ptx::named_bar_sync(bar_id, 128);
@@ -527,8 +595,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             gsel ^= 1;
           }
         }
+      } else if constexpr (Cfg::kXpose) {
+        // ---------- element-wise epilogue, fp32 output, coalesced through a per-warp smem transpose ----------
+        // phase 1: lane = accumulator row; (acc + bias, activation) -> 8 x 16 B into row `lane` of the warp's patch
+        //          (16-byte chunk j of row r sits at j ^ (r & 7): conflict-free for both phases)
+        // phase 2: lane = (row 4i + lane/8, chunk lane%8): LDS.128 + residual LDG.128 + add + STG.128, i = 0..7
+        //          -> a warp instruction covers 4 rows x 128 contiguous bytes
+        const uint32_t patch = ptx::smem_u32(xpose + e * 4096);
+        const int sub_row = lane >> 3, chunk16 = lane & 7;
+        const int64_t row0 = (int64_t)m_blk * kBM + quad * 32;
+        uint32_t rbuf[2][32];
+        ptx::tmem_ld_32x32(taddr, rbuf[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = colh + c * 32;
+          const bool active = col0 < p.N;  // warp-uniform
+          ptx::tmem_ld_wait();
+          if (c + 1 < 4) ptx::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);  // prefetch
+          const uint32_t(&r)[32] = rbuf[c & 1];
+          if (c == 3) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_tmem(acc);
+          }
+          if (!active) continue;
+          // residual rows of phase 2 are requested first: their latency hides behind phase 1
+          uint4 rres[8];
+          if (EPI == NRB_EPI_RESIDUAL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int64_t rr = row0 + 4 * i + sub_row;
+              rres[i] = make_uint4(0, 0, 0, 0);
+              if (rr < M) {
+                const int64_t rrow = p.res_map != nullptr ? (int64_t)p.res_map[rr] : rr;
+                if (p.res_dtype == NRB_F32) {
+                  rres[i] = ldg_stream_128(reinterpret_cast<const float*>(p.res) + rrow * p.ldres + col0 + chunk16 * 4);
+                } else {
+                  const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                                  rrow * p.ldres + col0 + chunk16 * 4);
+                  rres[i] = make_uint4(h.x << 16, h.x & 0xffff0000u, h.y << 16, h.y & 0xffff0000u);
+                }
+              }
+            }
+          }
+          float v[32];
+          activate_chunk<EPI == NRB_EPI_RESIDUAL ? NRB_EPI_NONE : EPI>(r, p, row, col0, row_ok, v);
+          __syncwarp();  // the previous chunk's phase-2 reads of the patch are complete
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(patch + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]),
+                         __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + sub_row;
+            const int64_t rr = row0 + rl;
+            uint4 a;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                         : "r"(patch + (uint32_t)rl * 128u + (uint32_t)((chunk16 ^ (rl & 7)) << 4)));
+            float4 o = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+            if (EPI == NRB_EPI_RESIDUAL) {
+              o.x += __uint_as_float(rres[i].x);
+              o.y += __uint_as_float(rres[i].y);
+              o.z += __uint_as_float(rres[i].z);
+              o.w += __uint_as_float(rres[i].w);
+            }
+            if (rr < M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + rr * p.ldy + col0 + chunk16 * 4) = o;
+          }
+        }
       } else {
-        // ---------- element-wise epilogue, fp32 output with 128-bit global stores ----------
+        // ---------- element-wise epilogue, fp32 output with 128-bit global stores (GEGLU + fp32 only) ----------
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int col0 = colh + c * 32;
@@ -539,17 +676,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (row_ok) {
             float v[32];
             activate_chunk<EPI>(r, p, row, col0, row_ok, v);
-            if (kGeglu) {
-              float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + (col0 >> 1);
+            float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + (col0 >> 1);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              float* y = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
         ptx::tc_fence_before();
@@ -635,11 +765,9 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   const int cs = CG == 2 ? 2 : (Cfg::kSoftmax ? p.cluster : 1);
   const int n_split = CG == 2 ? 1 : cs;
   const int64_t units = ((p.M + kBM * CG - 1) / (kBM * CG)) * (int64_t)(((p.N + BN - 1) / BN) / n_split);
-  const int max_units = sm_count_cached() / cs;
-  const int grid = (int)std::min<int64_t>(units, max_units) * cs;
+  int max_units = sm_count_cached() / cs;
   if (cs > 1 || Cfg::kSoftmax) {  // softmax always launches as a cluster (st.async / mapa need one, even of size 1)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
@@ -650,8 +778,27 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // A persistent kernel must not ask for more clusters than can be co-resident: the GPCs hold 16 / 18 / 20 SMs, so
+    // clusters of 4 fit 33 times (132 SMs), not 148 / 4 = 37 -- the 4 surplus clusters would run as a second wave
+    // after the first one has finished all of its tiles (cluster-of-4 softmax: 517 -> ~1000 TFLOP/s).
+    static int max_clusters[64][9] = {};
+    if (cs > 2 && dev >= 0 && dev < 64 && cs <= 8) {
+      if (max_clusters[dev][cs] == 0) {
+        cfg.gridDim = dim3(max_units * cs);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+          (void)cudaGetLastError();
+          n = max_units;
+        }
+        max_clusters[dev][cs] = n;
+      }
+      max_units = std::min(max_units, max_clusters[dev][cs]);
+    }
+    const int grid = (int)std::min<int64_t>(units, max_units) * cs;
+    cfg.gridDim = dim3(grid);
     NRB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mw, my, p));
   } else {
+    const int grid = (int)std::min<int64_t>(units, max_units);
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, my, p);
   }
   note_launch();

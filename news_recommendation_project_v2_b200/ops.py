@@ -221,11 +221,15 @@ def latent_fold(sd: dict, heads: int, dim_head: int, precision: torch.dtype, dev
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib.nrb_latent_fold(prec, dim, heads, dim_head, L, ptr(lat), ptr(lnc_w), ptr(lnc_b), ptr(wq), ptr(wkv),
                               ptr(wout), ptr(a), ptr(b), ptr(ws), ws_bytes, stream_ptr()), "nrb_latent_fold")
-    # GEGLU: interleave the value / gate halves of net.0 so one accumulator tile holds both
+    # GEGLU: interleave the value / gate halves of net.0 in PAIRS (a0,a1,g0,g1,a2,a3,g2,g3,...) so that one
+    # accumulator tile holds both and neighbouring columns form packed fp32 pairs (FFMA2 epilogue)
     w1, b1 = f32(p1 + "fn.net.0.weight"), f32(p1 + "fn.net.0.bias")
     half = w1.shape[0] // 2
-    w1i = torch.stack([w1[:half], w1[half:]], dim=1).reshape(2 * half, dim).to(precision).contiguous()
-    b1i = torch.stack([b1[:half], b1[half:]], dim=1).reshape(2 * half).contiguous()
+    if half % 2:
+        raise _lib.NrbError("GEGLU width must be even")
+    w1i = torch.stack([w1[:half].view(half // 2, 2, dim), w1[half:].view(half // 2, 2, dim)], dim=1) \
+        .reshape(2 * half, dim).to(precision).contiguous()
+    b1i = torch.stack([b1[:half].view(half // 2, 2), b1[half:].view(half // 2, 2)], dim=1).reshape(2 * half).contiguous()
     t = {
         "a": a, "b": b,
         "ln1_w": f32(p0 + "norm.weight"), "ln1_b": f32(p0 + "norm.bias"),

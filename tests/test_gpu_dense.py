@@ -32,7 +32,8 @@ def _ref_linear(a, w, bias, epi, res):
     elif epi == 3:
         y = y + res.double()
     elif epi == 4:
-        a_, g_ = y[:, 0::2], y[:, 1::2]  # interleaved (a0,g0,a1,g1,...)
+        y4 = y.reshape(y.shape[0], -1, 4)  # interleaved in pairs (a0,a1,g0,g1,a2,a3,g2,g3,...)
+        a_, g_ = y4[:, :, 0:2].reshape(y.shape[0], -1), y4[:, :, 2:4].reshape(y.shape[0], -1)
         y = a_ * 0.5 * g_ * (1 + torch.erf(g_ / math.sqrt(2)))
     return y
 
