@@ -78,8 +78,9 @@ def parse_args():
     ap.add_argument("--workload", choices=["cfg4", "cfg5"], default="cfg4",
                     help="cfg4 = headline (replicated table); cfg5 = long-history stress, row-sharded table")
     ap.add_argument("--table-rows", type=int, default=0, help="cfg5: total table rows (default 1.25 M per GPU)")
-    ap.add_argument("--gather", choices=["p2p", "dma", "nccl", "none"], default="dma",
-                    help="cfg5: all-gather implementation (none = transform only, for diagnosis: results invalid)")
+    ap.add_argument("--gather", choices=["auto", "p2p", "dma", "nccl", "nvls", "none"], default="auto",
+                    help="cfg5 / strong: all-gather implementation (auto = nvls when NVLink multicast is available, "
+                         "else dma; none = transform only, for diagnosis: results invalid)")
     ap.add_argument("--chunk-rows", type=int, default=0, help="cfg5: table rows transformed + pushed per chunk")
     ap.add_argument("--strong-chunks", type=int, default=4, help="strong leg: chunks per rank of the row transform")
     return ap.parse_args()
@@ -478,7 +479,7 @@ def leg_strong(args, D, model, eng_weak, weak_ms_step, peaks):
     r0, r1 = table_shard_bounds(N_ROWS, world)[rank]
     chunk = max(256, -(-(r1 - r0) // max(1, args.strong_chunks)))
     eng = ShardedTableEngine(table[r0:r1], N_ROWS, model, precision=args.precision, device=dev, gather=args.gather
-                             if args.gather != "none" else "dma", chunk_rows=chunk, cand_table=table)
+                             if args.gather != "none" else "auto", chunk_rows=chunk, cand_table=table)
     scores = torch.empty(n_c, dtype=torch.float32, device=dev)
     ranks = torch.empty(n_c, dtype=torch.int32, device=dev)
     flag = ops.new_err_flag(dev)
@@ -549,7 +550,7 @@ def leg_cfg5(args, D, peaks, standalone: bool = False):
     lib = _lib.load()
     d, L, h_max = 1024, 1024, 200
     n_rows = args.table_rows if args.table_rows > 0 else 1_250_000 * world
-    chunk_rows = args.chunk_rows if args.chunk_rows > 0 else int(os.environ.get("NRB200_CFG5_CHUNK_ROWS", "65536"))
+    chunk_rows = args.chunk_rows if args.chunk_rows > 0 else int(os.environ.get("NRB200_CFG5_CHUNK_ROWS", "32768"))
     n_imp = max(1, 1_048_576 // world) if (args.impressions == 2_400_000 or not standalone) else args.impressions
     model = LatentAttentionModel(dim=d, num_latents=L, precision="bf16").eval()
     model.load_state_dict(syn.make_latent_state_dict(d, L, seed=1234))
@@ -603,7 +604,7 @@ def leg_cfg5(args, D, peaks, standalone: bool = False):
 
     # ---- sharded == locally recomputed, bit for bit, on a sample of PEER-owned rows -----------------
     identical = None
-    if args.gather != "none":
+    if eng.gather != "none":
         peer = (rank + 1) % world
         p0, p1 = table_shard_bounds(n_rows, world)[peer]
         gs = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -630,7 +631,7 @@ def leg_cfg5(args, D, peaks, standalone: bool = False):
         "higher_is_better": True, "scaling": "weak" if args.table_rows <= 0 else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "long-history stress (BASELINE configs[4]): latent-attention user encoder, table "
-                               "row-sharded, per-shard transform + all-gather (%s) + gather/pool/cosine/rank" % args.gather,
+                               "row-sharded, per-shard transform + all-gather (%s) + gather/pool/cosine/rank" % eng.gather,
                    "table_rows": n_rows, "rows_per_gpu": r1 - r0, "impressions_per_gpu": n_imp, "dim": d, "latents": L,
                    "history_max": h_max, "sum_history": n_h, "sum_candidates": n_c, "chunk_rows": chunk_rows},
         "gpu_launches": int(launches),

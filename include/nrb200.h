@@ -236,6 +236,28 @@ int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride, int64_t n_
 int nrb_push_bytes(const void* src, int64_t n_bytes, void* const* dst_ptrs_host, int world,
                    int64_t dst_byte_offset, nrb_stream_t stream);
 
+/* Fused compute + collective variant: the all-gather rides INSIDE the tensor-core kernels.  nrb_push_attach
+ * registers up to 3 row segments (finished rows of the previous chunk) whose destination `mc_dst` is the NVLink
+ * MULTICAST address (NVLS) of the table every rank holds; the next `spread` tcgen05 GEMM launches issued by this
+ * host thread (nrb_linear / nrb_final_attention_rows / nrb_latent_forward on the bf16 path) each carry
+ * ceil(n_rows / spread) rows of every segment: the otherwise idle fourth control warp of each persistent GEMM CTA
+ * streams them out with one multimem.st per 16 bytes (fp32 -> bf16 rounding on the way if asked) while the MMA and
+ * epilogue warps work, so the transfer needs no extra SM, no copy engine and no second kernel.  nrb_push_flush
+ * sends whatever no GEMM picked up with a small store-only kernel (also the way to push the last chunk). */
+typedef struct nrb_push_seg {
+  const void* src;         /* local rows [n_rows, dim]                                   */
+  int src_dtype;           /* NRB_F32 | NRB_BF16                                         */
+  int64_t src_stride;      /* elements                                                   */
+  void* mc_dst;            /* multicast address of the destination table (row 0)         */
+  int dst_dtype;           /* NRB_BF16 | NRB_F32 (same as src, or fp32 -> bf16)          */
+  int64_t dst_stride;      /* elements                                                   */
+  int64_t dst_row_offset;  /* first destination row                                      */
+  int64_t n_rows;
+  int dim;
+} nrb_push_seg;
+int nrb_push_attach(const nrb_push_seg* segs, int n_segs, int spread);
+int nrb_push_flush(nrb_stream_t stream);
+
 /* ---- behaviour log -> CSR index builder (host; the step in front of the hot path) ------------------
  * replaces data_utils.py:168-232 split_impressions_and_history.  `impressions` / `history` are
  * '\n'-separated UTF-8 buffers with one line per behaviour row (empty history line = no history).

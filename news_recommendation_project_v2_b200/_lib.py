@@ -33,6 +33,14 @@ class LatentWeights(C.Structure):
     ]
 
 
+class PushSeg(C.Structure):
+    """struct nrb_push_seg (include/nrb200.h)."""
+
+    _fields_ = [("src", C.c_void_p), ("src_dtype", C.c_int), ("src_stride", C.c_int64), ("mc_dst", C.c_void_p),
+                ("dst_dtype", C.c_int), ("dst_stride", C.c_int64), ("dst_row_offset", C.c_int64),
+                ("n_rows", C.c_int64), ("dim", C.c_int)]
+
+
 # name -> (restype, argtypes); must list EVERY symbol of include/nrb200.h (tests check this)
 PROTOTYPES = {
     "nrb_version": (C.c_char_p, []),
@@ -66,6 +74,8 @@ PROTOTYPES = {
     "nrb_push_rows": (_i32, [_c_void_p, _i32, _i64, _i64, _i32, C.POINTER(C.c_void_p), _i32, _i32, _i64, _i64,
                              _c_void_p]),
     "nrb_push_bytes": (_i32, [_c_void_p, _i64, C.POINTER(C.c_void_p), _i32, _i64, _c_void_p]),
+    "nrb_push_attach": (_i32, [C.POINTER(PushSeg), _i32, _i32]),
+    "nrb_push_flush": (_i32, [_c_void_p]),
     "nrb_csr_build": (_c_void_p, [C.c_char_p, _i64, C.c_char_p, _i64, _i64]),
     "nrb_csr_sizes": (_i32, [_c_void_p, C.POINTER(_i64)]),
     "nrb_csr_export": (_i32, [_c_void_p] * 8),

@@ -13,6 +13,9 @@
 //               so the epilogue of tile i overlaps the mainloop of tile i+1; tcgen05.commit frees smem
 //               stages and publishes accumulators.
 //   warp 2    : TMEM allocator.
+//   warp 3    : all-gather carrier -- when a push job is attached (row-sharded table build) it streams finished
+//               rows of the PREVIOUS chunk to every rank's table with NVLink multicast stores (multimem.st),
+//               so the collective overlaps the tensor-core work inside the same kernel.
 //   warps 4-11: epilogue     -- two warps per TMEM lane quadrant, 128 accumulator columns each:
 //               tcgen05.ld (32 lanes x 32 columns) -> registers -> fused math -> either
 //                 * bf16 outputs: 128B-swizzled staging tile in smem -> TMA store (coalesced, async), or
@@ -84,6 +87,7 @@ struct GemmParams {
   int group;        // softmax: padded group width Lp (power of two >= 32)
   int group_valid;  // softmax: valid columns per group (L <= Lp)
   int cluster;      // softmax: CTAs per cluster = max(1, Lp / 256)
+  PushJob push;     // rows of an earlier result that the spare warp multicasts to every rank while the GEMM runs
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -391,6 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== all-gather carrier (NVLS multicast stores) =====================
+    if (p.push.n_seg > 0) push_job_warp(p.push, blockIdx.x, gridDim.x, lane);
   } else if (warp >= kCtrlWarps && (warp - kCtrlWarps) < 4 * kHalves) {
     // ===================== epilogue =====================
     const int e = warp - kCtrlWarps;
@@ -888,6 +895,7 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   p.group = group;
   p.group_valid = group_valid;
   p.cluster = cluster;
+  take_push_share(&p.push);  // a share of the pending all-gather segments rides along (nrb_push_attach)
   if (softmax) return launch_gemm<256, NRB_EPI_SOFTMAX, true>(ma, mw, my, p, st);
   if (small_n) {
     return out_dtype == NRB_BF16 ? dispatch_epi<128, true>(epi, ma, mw, my, p, st)

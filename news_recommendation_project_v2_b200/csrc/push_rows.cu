@@ -53,9 +53,93 @@ push_rows_kernel(const PushParams p) {
   }
 }
 
+// ---- multicast pushes that ride inside the GEMM kernels ----------------------------------------------------------
+// Pending segments of this host thread.  Every tcgen05 GEMM launch takes rows [done, done + share) of each segment,
+// share = ceil(rows / spread): after `spread` launches everything is on its way; nrb_push_flush sends the rest.
+struct PendingPush {
+  PushSeg seg[kMaxPushSegs];
+  int64_t done[kMaxPushSegs];
+  int64_t share[kMaxPushSegs];
+  int n_seg = 0;
+};
+static thread_local PendingPush g_pending;
+
+static void cut_share(PushJob* job, bool everything) {
+  job->n_seg = 0;
+  PendingPush& q = g_pending;
+  bool left = false;
+  for (int i = 0; i < q.n_seg; ++i) {
+    const int64_t remain = q.seg[i].n_rows - q.done[i];
+    if (remain <= 0) continue;
+    const int64_t take = everything ? remain : std::min<int64_t>(remain, q.share[i]);
+    PushSeg sg = q.seg[i];
+    sg.src += q.done[i] * sg.src_stride_bytes;
+    sg.dst += q.done[i] * sg.dst_stride_bytes;
+    sg.n_rows = take;
+    job->seg[job->n_seg++] = sg;
+    q.done[i] += take;
+    left = left || q.done[i] < q.seg[i].n_rows;
+  }
+  if (!left) q.n_seg = 0;
+}
+
+void take_push_share(PushJob* job) { cut_share(job, false); }
+
+__global__ void __launch_bounds__(128)
+push_multicast_kernel(const PushJob job) {
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  push_job_warp(job, warp_id, n_warps, threadIdx.x & 31);
+}
+
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_push_attach(const nrb_push_seg* segs, int n_segs, int spread) {
+  NRB_REQUIRE(n_segs >= 0 && n_segs <= kMaxPushSegs, "nrb_push_attach: at most %d segments", kMaxPushSegs);
+  NRB_REQUIRE(spread >= 1, "nrb_push_attach: spread must be >= 1");
+  NRB_REQUIRE(g_pending.n_seg == 0, "nrb_push_attach: earlier segments are still pending (call nrb_push_flush)");
+  NRB_REQUIRE(n_segs == 0 || segs != nullptr, "nrb_push_attach: null pointer");
+  for (int i = 0; i < n_segs; ++i) {
+    const nrb_push_seg& u = segs[i];
+    NRB_REQUIRE(u.src && u.mc_dst && u.n_rows >= 0 && u.dim > 0, "nrb_push_attach: bad segment %d", i);
+    NRB_REQUIRE((u.src_dtype == NRB_F32 || u.src_dtype == NRB_BF16) && (u.dst_dtype == NRB_F32 || u.dst_dtype == NRB_BF16),
+                "nrb_push_attach: bad dtype");
+    NRB_REQUIRE(u.src_dtype == u.dst_dtype || (u.src_dtype == NRB_F32 && u.dst_dtype == NRB_BF16),
+                "nrb_push_attach: only same-dtype or fp32 -> bf16 pushes");
+    const int ses = u.src_dtype == NRB_F32 ? 4 : 2, des = u.dst_dtype == NRB_F32 ? 4 : 2;
+    NRB_REQUIRE((u.dim * des) % 16 == 0 && (u.src_stride * ses) % 16 == 0 && (u.dst_stride * des) % 16 == 0 &&
+                    (reinterpret_cast<uintptr_t>(u.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(u.mc_dst) & 15) == 0,
+                "nrb_push_attach: rows must be 16-byte aligned multiples");
+    PushSeg& sg = g_pending.seg[i];
+    sg.src = (const char*)u.src;
+    sg.dst = (char*)u.mc_dst + u.dst_row_offset * u.dst_stride * des;
+    sg.n_rows = u.n_rows;
+    sg.src_stride_bytes = u.src_stride * ses;
+    sg.dst_stride_bytes = u.dst_stride * des;
+    sg.vecs_per_row = u.dim * des / 16;
+    sg.f32_to_bf16 = (u.src_dtype == NRB_F32 && u.dst_dtype == NRB_BF16) ? 1 : 0;
+    g_pending.done[i] = 0;
+    g_pending.share[i] = (u.n_rows + spread - 1) / spread;
+  }
+  g_pending.n_seg = n_segs;
+  return NRB_OK;
+}
+
+extern "C" int nrb_push_flush(nrb_stream_t stream) {
+  PushJob job;
+  cut_share(&job, true);
+  if (job.n_seg == 0) return NRB_OK;
+  int64_t vecs = 0;
+  for (int i = 0; i < job.n_seg; ++i) vecs += job.seg[i].n_rows * job.seg[i].vecs_per_row;
+  const int64_t want = (vecs + 128 * 4 - 1) / (128 * 4);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count_cached() * 8));
+  push_multicast_kernel<<<grid, 128, 0, as_stream(stream)>>>(job);
+  note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
 
 extern "C" int nrb_push_rows(const void* src, int src_dtype, int64_t src_stride, int64_t n_rows, int dim,
                              void* const* dst_ptrs_host, int world, int dst_dtype, int64_t dst_row_offset,

@@ -336,6 +336,25 @@ def convert_rows(src: torch.Tensor, out_dtype: torch.dtype, out: Optional[torch.
     return out
 
 
+def push_attach(segments: list, spread: int) -> None:
+    """Attach all-gather segments to the next `spread` tensor-core GEMM launches (nrb_push_attach).
+    `segments`: [(src [rows, dim] CUDA tensor, multicast_ptr of the destination table, dst dtype, first dst row,
+    dst row stride in elements)]; the GEMMs' spare warps multicast the rows to every rank (NVLS)."""
+    arr = (_lib.PushSeg * max(len(segments), 1))()
+    for i, (src, mc_ptr, dst_dtype, row0, dst_stride) in enumerate(segments):
+        require_device(src.device)
+        if src.dim() != 2 or src.stride(1) != 1:
+            raise _lib.NrbError("push segment source must be a [rows, dim] tensor with unit inner stride")
+        arr[i] = _lib.PushSeg(ptr(src), dtype_code(src.dtype), src.stride(0), int(mc_ptr), dtype_code(dst_dtype),
+                              int(dst_stride), int(row0), src.shape[0], src.shape[1])
+    check(load().nrb_push_attach(arr, len(segments), int(spread)), "nrb_push_attach")
+
+
+def push_flush() -> None:
+    """Send what no GEMM picked up with the store-only multicast kernel (nrb_push_flush)."""
+    check(load().nrb_push_flush(stream_ptr()), "nrb_push_flush")
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Row-wise LayerNorm (nrb_layer_norm): x [rows, dim] fp32/bf16, gamma/beta fp32."""

@@ -14,6 +14,9 @@ transform of chunk i+1 (the store-only kernel co-resides with the persistent GEM
 register footprint leaves room).  `gather="dma"` = `nrb_push_bytes`: the transform writes its chunk into
 the local copy and the copy engines forward it to the peers, which needs no SM resources at all.
 `gather="nccl"` keeps the plain `all_gather_into_tensor` variant for comparison / non-P2P setups.
+`gather="nvls"` is the fused compute + collective form: the rows of chunk i are multicast to every rank (one
+`multimem.st` per 16 bytes through the NVSwitch) by the SPARE CONTROL WARP of the persistent tcgen05 GEMM CTAs that
+compute chunk i+1 (`nrb_push_attach`), so the all-gather costs no copy engine, no extra kernel and no SM.
 """
 from __future__ import annotations
 
@@ -30,7 +33,7 @@ from .sharding import table_shard_bounds
 
 class ShardedTableEngine(ScoringEngine):
     def __init__(self, local_rows: torch.Tensor, n_rows_total: int, model: torch.nn.Module, precision=None,
-                 device: Optional[torch.device] = None, group=None, gather: str = "dma", chunk_rows: int = 32768,
+                 device: Optional[torch.device] = None, group=None, gather: str = "auto", chunk_rows: int = 32768,
                  cand_table: Optional[torch.Tensor] = None):
         """`cand_table`: the full RAW table, already resident on this device in the engine dtype (BASELINE
         configs[3] sharded over ranks: the table is replicated, only its per-row transform is partitioned).
@@ -63,14 +66,21 @@ class ShardedTableEngine(ScoringEngine):
                                            or cand_table.device != dev):
                 raise _lib.NrbError("cand_table must be the full [n_rows, dim] table on the engine device / dtype")
             self._tick = torch.zeros(1, dtype=torch.int32, device=dev)
-            if gather in ("p2p", "dma", "none"):
+            if gather in ("p2p", "dma", "none", "nvls", "auto"):
                 import torch.distributed._symmetric_memory as symm_mem
 
-                self._full, self._ptrs = {}, {}
+                self._full, self._ptrs, self._mc = {}, {}, {}
                 for nm in self._names:
                     t = symm_mem.empty((n, d), dtype=self.dtype, device=dev)
                     h = symm_mem.rendezvous(t, self.group)
                     self._full[nm], self._ptrs[nm] = t, list(h.buffer_ptrs)
+                    self._mc[nm] = int(getattr(h, "multicast_ptr", 0) or 0)
+                if gather == "nvls" and not all(self._mc.values()):
+                    raise _lib.NrbError("gather='nvls' needs NVLink multicast (NVLS) support for symmetric memory; "
+                                        "use gather='dma'")
+                if gather == "auto":  # fused in-GEMM multicast where the fabric offers it, copy engines otherwise
+                    gather = "nvls" if all(self._mc.values()) else "dma"
+                    self.gather = gather
             elif gather == "nccl":
                 ns = table_shard_bounds(n, self.world)[0][1]
                 self._full = {nm: torch.empty(self.world * ns, d, dtype=self.dtype, device=dev) for nm in self._names}
@@ -105,6 +115,13 @@ class ShardedTableEngine(ScoringEngine):
                     self._fa_weights_key = fp
                 w = self._fa_weights
             compute = torch.cuda.current_stream()
+            if self.gather == "nvls":
+                self._build_nvls(local_rows, fw if latent else None, None if latent else w)
+                self._stream_barrier()
+                self.cand = self._cand_table if self._cand_table is not None else full["cand"][:n]
+                self.hist_x = full["hist_x"][:n]
+                self.hist_e = None if latent else full["hist_e"][:n]
+                return
             dma = self.gather in ("dma", "none")
             if self.gather == "none":  # diagnosis only: peers are never written (every destination = local copy)
                 ptrs = {nm: [p[self.rank]] * self.world for nm, p in ptrs.items()}
@@ -180,6 +197,34 @@ class ShardedTableEngine(ScoringEngine):
             self.cand = self._cand_table if self._cand_table is not None else full["cand"][:n]
             self.hist_x = full["hist_x"][:n]
             self.hist_e = None if latent else full["hist_e"][:n]
+
+    def _build_nvls(self, local_rows: torch.Tensor, fw, w) -> None:
+        """Fused compute + collective build: chunk i's rows are multicast to every rank by the spare warp of the GEMM
+        CTAs that compute chunk i+1; the last chunk leaves through the store-only flush kernel."""
+        r0, r1 = self._bounds
+        d, dev, mc = self.dim, self.device, self._mc
+        prev = None
+        for c0 in range(0, r1 - r0, self.chunk_rows):
+            c1 = min(r1 - r0, c0 + self.chunk_rows)
+            chunk = local_rows[c0:c1].to(dev, non_blocking=True)
+            if chunk.dtype != self.dtype:
+                chunk = ops.convert_rows(chunk.contiguous(), self.dtype)
+            chunk = chunk.contiguous()
+            g0 = r0 + c0
+            if prev is not None:
+                ops.push_attach(prev, 4 if self._latent else 5)  # the GEMM launches of one internal row block
+            segs = [(chunk, mc["cand"], self.dtype, g0, d)] if "cand" in self._names else []
+            if self._latent:
+                out = ops.latent_forward(fw, chunk.view(c1 - c0, 1, d), None, max_tokens=LATENT_MAX_TOKENS)
+                segs.append((out.view(c1 - c0, d), mc["hist_x"], self.dtype, g0, d))  # fp32 -> table dtype on the way
+            else:
+                x, e = ops.final_attention_rows(chunk, w, self.dtype)
+                segs += [(x, mc["hist_x"], self.dtype, g0, d), (e, mc["hist_e"], self.dtype, g0, d)]
+            ops.push_flush()  # rows of the previous chunk that no GEMM picked up
+            prev = segs  # keeps the sources alive until the next chunk's kernels are queued behind them
+        if prev is not None:
+            ops.push_attach(prev, 1)
+            ops.push_flush()
 
     def _stream_barrier(self) -> None:
         """Device-side barrier: a 4-byte NCCL all-reduce ordered on the CURRENT stream.  It completes on a rank only
