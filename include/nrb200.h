@@ -73,6 +73,11 @@ int nrb_dense_rank(const float* scores, const int64_t* offsets, int64_t n_groups
 int nrb_dense_rank_f64(const double* scores, const int64_t* offsets, int64_t n_groups,
                        int32_t* ranks, nrb_stream_t stream);
 
+/* int32 dense ranks -> int16 on the device, for hosts that want the ranks of a large evaluation over PCIe at 2
+ * bytes per candidate (a dense rank never exceeds the candidate count of its impression).  A value above 32767
+ * saturates and sets bit 1 of *err_flag. */
+int nrb_narrow_ranks(const int32_t* ranks, int16_t* ranks16, int64_t n, int32_t* err_flag, nrb_stream_t stream);
+
 /* ---- Stage C: per-impression top-k ordering --------------------------------------------------
  * the order evaluation.py:14,28 derives from the ranks (argsort of the scores, descending), made
  * explicit: out_idx[g, p] = position inside group g of the candidate at place p (p < k), equal scores in

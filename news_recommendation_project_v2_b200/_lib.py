@@ -50,6 +50,7 @@ PROTOTYPES = {
     "nrb_kernel_launches": (C.c_longlong, []),
     "nrb_dense_rank": (_i32, [_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
     "nrb_dense_rank_f64": (_i32, [_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
+    "nrb_narrow_ranks": (_i32, [_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
     "nrb_topk_order": (_i32, [_c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p]),
     "nrb_gather_collate": (_i32, [_c_void_p, _i32, _i64, _i32, _i64, _c_void_p, _c_void_p, _i64, _i32,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

@@ -453,9 +453,48 @@ gather_collate_kernel(const char* table, int64_t n_rows, int row_bytes, int64_t 
   }
 }
 
+// int32 dense ranks -> int16 (halves the device->host bytes of the ranks; a rank never exceeds the candidate count
+// of its impression).  Values that do not fit set bit 1 of *err_flag and saturate.
+__global__ void __launch_bounds__(256)
+narrow_ranks_kernel(const int32_t* src, int16_t* dst, int64_t n, int32_t* err_flag) {
+  const int64_t n8 = n / 8;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 a = *reinterpret_cast<const int4*>(src + i * 8), b = *reinterpret_cast<const int4*>(src + i * 8 + 4);
+    const int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bad |= v[2 * k] > 32767 || v[2 * k + 1] > 32767;
+      o[k] = (uint32_t)min(v[2 * k], 32767) | ((uint32_t)min(v[2 * k + 1], 32767) << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bad |= src[i] > 32767;
+    dst[i] = (int16_t)min(src[i], 32767);
+  }
+  if (bad) atomicOr(err_flag, 2);
+}
+
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_narrow_ranks(const int32_t* ranks, int16_t* ranks16, int64_t n, int32_t* err_flag,
+                                nrb_stream_t stream) {
+  NRB_REQUIRE(n >= 0, "nrb_narrow_ranks: n < 0");
+  if (n == 0) return NRB_OK;
+  NRB_REQUIRE(ranks && ranks16 && err_flag, "nrb_narrow_ranks: null pointer");
+  NRB_REQUIRE((reinterpret_cast<uintptr_t>(ranks) & 15) == 0 && (reinterpret_cast<uintptr_t>(ranks16) & 15) == 0,
+              "nrb_narrow_ranks: buffers must be 16-byte aligned");
+  const int64_t want = (n / 8 + 255) / 256 + 1;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 16);
+  narrow_ranks_kernel<<<grid, 256, 0, as_stream(stream)>>>(ranks, ranks16, n, err_flag);
+  note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
 
 template <typename V, int WARPS>
 static int launch_dense_rank(const V* scores, const int64_t* offsets, int64_t n_groups, int32_t* ranks,

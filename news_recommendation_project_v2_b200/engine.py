@@ -155,7 +155,9 @@ class ScoringEngine:
         """HOST (ideally pinned) CSR arrays in, HOST scores / ranks out, pipelined over impression chunks:
         index H2D (copy stream) | fused score+rank kernel (compute stream) | result D2H (copy-out stream).
 
-        hist_idx / cand_idx int32, hist_off / cand_off int64 [I+1] CPU tensors."""
+        hist_idx / cand_idx int32, hist_off / cand_off int64 [I+1] CPU tensors.  `ranks_out` may be int32 or int16:
+        int16 ranks are narrowed on the device and cross PCIe at 2 bytes per candidate (6 instead of 8 bytes of
+        results per candidate; a rank above 32767 raises OverflowError)."""
         dev = self.device
         n_imp = hist_off.numel() - 1
         assert cand_off.numel() - 1 == n_imp, "Number of rows should be consistent"
@@ -173,6 +175,8 @@ class ScoringEngine:
             ci_d = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
             sc_d = torch.empty(max(n_c, 1), dtype=torch.float32, device=dev)
             rk_d = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
+            narrow = ranks_out.dtype == torch.int16
+            rk16_d = torch.empty(max(n_c, 1) + 8, dtype=torch.int16, device=dev) if narrow else None
             flag = ops.new_err_flag(dev)
             ho_d = hist_off.to(dev, non_blocking=True)
             co_d = cand_off.to(dev, non_blocking=True)
@@ -195,12 +199,15 @@ class ScoringEngine:
                 cur.wait_event(ev)
                 ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hi_d, ho_d[i0:i1 + 1], ci_d,
                                co_d[i0:i1 + 1], n_c, want_ranks=True, err_flag=flag, out_scores=sc_d, out_ranks=rk_d)
+                if narrow and c1 > c0:
+                    a0 = c0 - (c0 % 8)  # 16-byte aligned window (the overlap rewrites identical values)
+                    ops.narrow_ranks(rk_d[a0:c1], rk16_d[a0:c1], flag)
                 done = torch.cuda.Event()
                 done.record(cur)
                 s_out.wait_event(done)
                 with torch.cuda.stream(s_out):
                     scores_out[c0:c1].copy_(sc_d[c0:c1], non_blocking=True)
-                    ranks_out[c0:c1].copy_(rk_d[c0:c1], non_blocking=True)
+                    ranks_out[c0:c1].copy_((rk16_d if narrow else rk_d)[c0:c1], non_blocking=True)
             s_out.synchronize()
             cur.synchronize()
             ops.raise_on_index_error(flag, "score_host")

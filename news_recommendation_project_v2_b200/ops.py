@@ -32,8 +32,11 @@ def new_err_flag(device) -> torch.Tensor:
 
 def raise_on_index_error(flag: torch.Tensor, what: str) -> None:
     """Host-side check of the device error flag (synchronises)."""
-    if int(flag.item()) & 1:
+    f = int(flag.item())
+    if f & 1:
         raise IndexError(f"{what}: row index out of range for the embedding table")
+    if f & 2:
+        raise OverflowError(f"{what}: a dense rank does not fit int16 (ask for int32 ranks)")
 
 
 def dense_rank(scores: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
@@ -49,6 +52,17 @@ def dense_rank(scores: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     fn = load().nrb_dense_rank if scores.dtype == torch.float32 else load().nrb_dense_rank_f64
     check(fn(ptr(scores), ptr(offsets), n_groups, ptr(ranks), stream_ptr()), "nrb_dense_rank")
     return ranks
+
+
+def narrow_ranks(ranks: torch.Tensor, out: torch.Tensor, err_flag: torch.Tensor) -> torch.Tensor:
+    """int32 dense ranks -> int16 (nrb_narrow_ranks); bit 1 of err_flag is set if a rank exceeds 32767."""
+    require_device(ranks.device)
+    _dev(ranks, "ranks", torch.int32)
+    _dev(out, "out", torch.int16)
+    if out.numel() != ranks.numel():
+        raise _lib.NrbError("narrow_ranks: size mismatch")
+    check(load().nrb_narrow_ranks(ptr(ranks), ptr(out), ranks.numel(), ptr(err_flag), stream_ptr()), "nrb_narrow_ranks")
+    return out
 
 
 def topk_order(scores: torch.Tensor, offsets: torch.Tensor, k: int) -> torch.Tensor:

@@ -157,6 +157,30 @@ def test_apply_token_attn_from_token_store(tmp_path):
     np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-3, rtol=0)
 
 
+def test_packed_token_file_pipeline_equals_padded_forward(tmp_path):
+    """Packed token FILE -> pinned double-buffered chunks -> forward_packed == padded + masked forward on the same
+    (bf16) tokens, bit for bit, whatever the chunk size; empty items give NaN rows."""
+    from news_recommendation_project_v2_b200.token_store import apply_token_attn_packed, write_packed_tokens
+    m = _model(256, 64, 21, "bf16", heads=4, dim_head=64)
+    g = torch.Generator().manual_seed(5)
+    items = [torch.randn(int(n), 256, generator=g).to(torch.bfloat16) for n in torch.randint(1, 40, (83,), generator=g)]
+    items[17] = items[17][:0]  # an empty item
+    path = str(tmp_path / "tok.nrbtok")
+    write_packed_tokens(path, items, 256)
+    S = max(t.shape[0] for t in items)
+    x = torch.zeros(len(items), S, 256, dtype=torch.bfloat16)
+    mask = torch.zeros(len(items), S, dtype=torch.int32)
+    for i, t in enumerate(items):
+        x[i, :t.shape[0]] = t
+        mask[i, :t.shape[0]] = 1
+    want = m(x.cuda(), mask.cuda()).cpu()
+    keep = [i for i in range(len(items)) if i != 17]
+    for chunk in (40, 333, 1 << 20):
+        got = apply_token_attn_packed(m, path, chunk_tokens=chunk, copy_threads=3)
+        assert got.is_pinned() and got.shape == (83, 256)
+        assert torch.isnan(got[17]).all() and torch.equal(got[keep], want[keep])
+
+
 def test_packed_all_empty_items_give_nan():
     """A chunk whose items are all empty returns NaN rows like the reference's 0/0 masked mean, never
     uninitialised memory."""

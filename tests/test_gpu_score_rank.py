@@ -221,3 +221,26 @@ def test_cached_engine_never_returns_a_stale_table(ops):
     engine._engine_cache[key] = (e1, __import__("weakref").ref(t2), None)
     e2 = engine.cached_engine(t1, model, precision="fp32")
     assert e2 is not e1
+
+
+def test_score_host_int16_ranks_equal_int32(ops):
+    """Host path with int16 ranks on the wire == int32 ranks; a rank above 32767 raises instead of wrapping."""
+    from news_recommendation_project_v2_b200.engine import ScoringEngine
+    from news_recommendation_project_v2_b200.modeling_utils import FinalAttention
+    model = FinalAttention(256, 512, precision="bf16").eval()
+    model.load_state_dict(syn.make_final_attention_state_dict(256, 512, seed=3))
+    table = syn.make_table(3000, 256, seed=1)
+    imp = syn.make_impressions(5000, 3000, h_max=50, cand="large", seed=9)
+    eng = ScoringEngine(table, model, precision="bf16")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    ho, co = t(syn.csr_offsets(imp.hist_len)), t(syn.csr_offsets(imp.cand_len))
+    s32, r32 = eng.score_host(t(imp.hist_idx), ho, t(imp.cand_idx), co, n_chunks=7)
+    r16 = torch.empty(r32.numel(), dtype=torch.int16).pin_memory()
+    s16, r16 = eng.score_host(t(imp.hist_idx), ho, t(imp.cand_idx), co, ranks_out=r16, n_chunks=7)
+    assert r16.dtype == torch.int16 and torch.equal(r16.to(torch.int32), r32) and torch.equal(s16, s32)
+    flag = ops.new_err_flag(torch.device("cuda"))
+    big = torch.arange(1, 40001, dtype=torch.int32, device="cuda")
+    out = ops.narrow_ranks(big, torch.empty(40000, dtype=torch.int16, device="cuda"), flag)
+    assert int(out[100]) == 101 and int(out[-1]) == 32767
+    with pytest.raises(OverflowError):
+        ops.raise_on_index_error(flag, "narrow")

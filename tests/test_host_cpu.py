@@ -232,6 +232,33 @@ def test_token_store_roundtrip(tmp_path):
         read_token_store(db, ids=[9])
 
 
+def test_packed_token_file_roundtrip(tmp_path):
+    """sqlite token store -> packed token file: same tokens (bf16-rounded), same item boundaries, mmap-able, chunk
+    bounds cover every item once and respect the token budget."""
+    from news_recommendation_project_v2_b200.token_store import (PackedTokenFile, convert_token_store,
+                                                                 write_packed_tokens, write_token_store)
+    g = torch.Generator().manual_seed(0)
+    items = [torch.randn(int(n), 64, generator=g).half() for n in torch.randint(0, 30, (57,), generator=g)]
+    db, path = str(tmp_path / "tok.sqlite"), str(tmp_path / "tok.nrbtok")
+    write_token_store(db, items)
+    n_items, n_tok = convert_token_store(db, path)
+    tf = PackedTokenFile(path)
+    assert (n_items, n_tok) == (57, sum(t.shape[0] for t in items)) == (tf.n_items, tf.n_tokens) and tf.dim == 64
+    assert tf.dtype == torch.bfloat16 and tf.offsets[0] == 0 and tf.offsets[-1] == n_tok
+    assert np.array_equal(np.diff(tf.offsets), [t.shape[0] for t in items])
+    assert torch.equal(tf.tokens(0, n_tok), torch.cat([t.to(torch.bfloat16) for t in items]))
+    bounds = tf.chunk_bounds(64)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 57 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+    assert all(tf.offsets[b] - tf.offsets[a] <= 64 for a, b in bounds)
+    # fp32 files and the header check
+    write_packed_tokens(str(tmp_path / "f32.nrbtok"), [t.float() for t in items[:5]], 64, torch.float32)
+    t32 = PackedTokenFile(str(tmp_path / "f32.nrbtok"))
+    assert t32.dtype == torch.float32 and torch.equal(t32.tokens(0, t32.n_tokens), torch.cat(items[:5]).float())
+    (tmp_path / "bad.nrbtok").write_bytes(b"x" * 8192)
+    with pytest.raises(ValueError):
+        PackedTokenFile(str(tmp_path / "bad.nrbtok"))
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver times beside ours) prints ONE JSON line with the contract keys;
     under torchrun every rank but 0 exits without work."""
