@@ -803,13 +803,20 @@ def leg_cfg3_e2e(dev):
         n_items, n_tok = write_packed_tokens(path, gen(), d)
         tf = PackedTokenFile(path)
         threads = max(1, min(16, (os.cpu_count() or 2) - 1))
-        out = apply_token_attn_packed(m, tf, copy_threads=threads)  # warm-up: page cache, workspace, pinned pools
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            out = apply_token_attn_packed(m, tf, copy_threads=threads, out=out)
-        dt = (time.perf_counter() - t) / reps
+        timings = {}
+        for mode in ("staged", "registered"):
+            if mode == "registered" and not tf.register():
+                timings[mode] = None
+                continue
+            out = apply_token_attn_packed(m, tf, copy_threads=threads)  # warm-up: page cache, workspace, pinned pools
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                out = apply_token_attn_packed(m, tf, copy_threads=threads, out=out)
+            timings[mode] = (time.perf_counter() - t) / reps
+        tf.unregister()
+        dt = min(v for v in timings.values() if v)
     finally:
         if os.path.exists(path):
             os.remove(path)
@@ -817,6 +824,8 @@ def leg_cfg3_e2e(dev):
     return {"value": round(n_items / dt, 1), "unit": "news/s", "seconds": round(dt, 4), "items": n_items,
             "valid_tokens": n_tok, "h2d_bytes_per_pass": int(h2d), "d2h_bytes_per_pass": int(n_items * d * 4),
             "achieved_h2d_gbs": round(h2d / dt / 1e9, 2), "copy_threads": threads, "file_on": base,
+            "seconds_staged_through_pinned_buffers": round(timings["staged"], 4),
+            "seconds_mapping_page_locked": None if timings["registered"] is None else round(timings["registered"], 4),
             "finite": bool(torch.isfinite(out).all()),
             "max_unit_norm_err": float((out.norm(dim=-1) - 1).abs().max()),
             "what": "packed token file (mmap, page cache) -> pinned double buffers -> H2D -> nrb_latent_forward_packed "

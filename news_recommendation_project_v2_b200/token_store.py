@@ -161,6 +161,37 @@ class PackedTokenFile:
         self.tokens_raw = np.memmap(path, dtype=npdt, mode="r", offset=tok_off, shape=(self.n_tokens, self.dim)) \
             if self.n_tokens else np.zeros((0, self.dim), dtype=npdt)
 
+    def register(self) -> bool:
+        """Page-lock the mapped token section for the GPU (cudaHostRegister, read-only): chunks then cross PCIe by DMA
+        straight from the page cache, with no staging copy.  Returns False when the driver refuses (then
+        `apply_token_attn_packed` stages through pinned buffers)."""
+        if getattr(self, "_registered", False):
+            return True
+        if not self.n_tokens or not torch.cuda.is_available():
+            return False
+        try:
+            rt = torch.cuda.cudart()
+            addr, nbytes = self.tokens_raw.ctypes.data, self.tokens_raw.nbytes
+            err = rt.cudaHostRegister(addr, nbytes, 8)  # cudaHostRegisterReadOnly
+            ok = int(err) == 0 if not isinstance(err, tuple) else int(err[0]) == 0
+            if ok:
+                probe = torch.from_numpy(self.tokens_raw[:1])
+                ok = bool(probe.is_pinned())
+                if not ok:
+                    rt.cudaHostUnregister(addr)
+            self._registered = ok
+        except Exception:
+            self._registered = False
+        return self._registered
+
+    def unregister(self) -> None:
+        if getattr(self, "_registered", False):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.tokens_raw.ctypes.data)
+            except Exception:
+                pass
+            self._registered = False
+
     def tokens(self, a: int, b: int) -> torch.Tensor:
         t = torch.from_numpy(np.array(self.tokens_raw[a:b]))  # a private, writable copy of the mapped rows
         return t.view(torch.bfloat16) if self.dtype == torch.bfloat16 else t
@@ -210,13 +241,30 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
         d2h_done = [None, None]
         pool = ThreadPoolExecutor(max_workers=max(1, copy_threads))
 
+        direct = bool(getattr(tf, "_registered", False))  # mapped section page-locked: DMA straight from the mapping
+
         def stage(k):
             i0, i1 = bounds[k]
             t0, t1 = int(tf.offsets[i0]), int(tf.offsets[i1])
             b = k & 1
+            n = t1 - t0
+            if direct:
+                if compute_done[b] is not None:
+                    s_in.wait_event(compute_done[b])
+                with torch.cuda.stream(s_in):
+                    if n:
+                        import warnings
+
+                        with warnings.catch_warnings():
+                            warnings.simplefilter("ignore")  # read-only mapping: torch never writes through this view
+                            src = torch.from_numpy(tf.tokens_raw[t0:t1])
+                        dbuf[b][:n].copy_(src.view(tdt) if src.dtype != tdt else src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                h2d_done[b] = ev
+                return n
             if h2d_done[b] is not None:
                 h2d_done[b].synchronize()  # the pinned buffer is free once its previous upload has finished
-            n = t1 - t0
             if n:
                 cuts = np.linspace(0, n, num=min(copy_threads, max(1, n // 4096)) + 1, dtype=np.int64)
                 list(pool.map(lambda ab: np.copyto(pinned_np[b][ab[0]:ab[1]], tf.tokens_raw[t0 + ab[0]:t0 + ab[1]]),

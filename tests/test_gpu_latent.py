@@ -179,6 +179,13 @@ def test_packed_token_file_pipeline_equals_padded_forward(tmp_path):
         got = apply_token_attn_packed(m, path, chunk_tokens=chunk, copy_threads=3)
         assert got.is_pinned() and got.shape == (83, 256)
         assert torch.isnan(got[17]).all() and torch.equal(got[keep], want[keep])
+    # zero-copy variant: the mapped token section page-locked for the GPU (skipped if the driver refuses)
+    from news_recommendation_project_v2_b200.token_store import PackedTokenFile
+    tf = PackedTokenFile(path)
+    if tf.register():
+        got = apply_token_attn_packed(m, tf, chunk_tokens=333)
+        assert torch.equal(got[keep], want[keep])
+        tf.unregister()
 
 
 def test_packed_all_empty_items_give_nan():
