@@ -94,6 +94,13 @@ int nrb_gather_collate(const void* table, int dtype, int64_t n_rows, int dim, in
                        const int32_t* idx, const int64_t* offsets, int64_t n_groups, int max_len,
                        void* emb_out, int32_t* mask_out, int32_t* err_flag, nrb_stream_t stream);
 
+/* attention_mask int32 [batch, seq] (any 0 / non-zero pattern) -> CSR form of the valid slots: idx_out[k] = flat
+ * position b*seq + s of the k-th valid slot (int32, capacity batch*seq), off_out int64 [batch + 1].  This is the
+ * mask handling of FinalAttention.forward / NewAttention.forward (modeling_utils.py:224, attention.py:270: weights
+ * times mask) turned into the index form nrb_score_rank pools over.  workspace: int32 [2*batch + 2]. */
+int nrb_mask_to_csr(const int32_t* mask, int64_t batch, int seq, int32_t* idx_out, int64_t* off_out,
+                    int32_t* workspace, nrb_stream_t stream);
+
 /* ---- Stage B+C fused: gather -> user vector -> cosine -> dense rank --------------------
  * replaces data_model_helper.py:112-131 (get_final_attention_eval: CPU gather in
  * DataLoader workers + user-encoder pooling), :200-230 (per-impression

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "nrb_topk_order": (_i32, [_c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p]),
     "nrb_gather_collate": (_i32, [_c_void_p, _i32, _i64, _i32, _i64, _c_void_p, _c_void_p, _i64, _i32,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "nrb_mask_to_csr": (_i32, [_c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "nrb_score_rank": (_i32, [_i32, _i32, _i32, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _i64, _c_void_p, _f32,
                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64,
                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

@@ -86,16 +86,7 @@ class NewAttention(nn.Module):
         with torch.cuda.device(dev):
             rows = embeddings.detach().to(device=dev, dtype=dtype).reshape(B * H, d).contiguous()
             x, e = self.row_tables(rows, dtype)
-            valid = attention_mask.to(dev) != 0
-            off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-            off[1:] = torch.cumsum(valid.sum(dim=1, dtype=torch.int64), 0)
-            idx = torch.nonzero(valid.reshape(-1), as_tuple=False).reshape(-1).to(torch.int32).contiguous()
-            if idx.numel() == 0:
-                idx = torch.zeros(1, dtype=torch.int32, device=dev)
-            zeros = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-            user, _, _ = ops.score_rank(_lib.POOL_FINAL_ATTENTION, x, e, x, idx, off,
-                                        torch.zeros(1, dtype=torch.int32, device=dev), zeros, 0, want_user=True,
-                                        want_ranks=False)
+            user = ops.pool_masked_rows(x, e, attention_mask)
         return user if in_dev.type == "cuda" else user.to(in_dev)
 
 

@@ -90,6 +90,12 @@ fill_row_map_kernel(const int32_t* mask, int64_t items, int seq, const int32_t* 
   }
 }
 
+// int32 item offsets -> int64 CSR offsets (the layout nrb_score_rank takes)
+__global__ void widen_offsets_kernel(const int32_t* in, int64_t n, int64_t* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+
 // pooled[i] = normalize(mean over the item's packed rows)  (latent_attention.py:165-170)
 // one CTA per item; thread t owns float4 columns t, t+256, ...
 template <int MAXV>
@@ -201,6 +207,30 @@ static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens,
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_mask_to_csr(const int32_t* mask, int64_t batch, int seq, int32_t* idx_out, int64_t* off_out,
+                               int32_t* workspace, nrb_stream_t stream) {
+  NRB_REQUIRE(batch >= 0 && seq > 0, "nrb_mask_to_csr: bad sizes");
+  NRB_REQUIRE(batch * (int64_t)seq < (int64_t)1 << 31, "nrb_mask_to_csr: batch * seq must fit int32");
+  NRB_REQUIRE(off_out != nullptr, "nrb_mask_to_csr: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (batch == 0) {
+    NRB_CUDA_CHECK(cudaMemsetAsync(off_out, 0, 8, st));
+    return NRB_OK;
+  }
+  NRB_REQUIRE(mask && idx_out && workspace, "nrb_mask_to_csr: null pointer");
+  int32_t* counts = workspace;                // [batch]
+  int32_t* item_off = workspace + batch;      // [batch + 1]
+  int32_t* total = workspace + 2 * batch + 1;  // [1]
+  const int g1 = (int)std::min<int64_t>((batch + 7) / 8, (int64_t)sm_count_cached() * 16);
+  count_valid_kernel<<<g1, 256, 0, st>>>(mask, batch, seq, counts); note_launch();
+  scan_items_kernel<<<1, 1024, 0, st>>>(counts, batch, item_off, total); note_launch();
+  fill_row_map_kernel<<<g1, 256, 0, st>>>(mask, batch, seq, item_off, idx_out); note_launch();
+  const int g2 = (int)std::min<int64_t>((batch + 1 + 255) / 256, (int64_t)sm_count_cached() * 4);
+  widen_offsets_kernel<<<g2, 256, 0, st>>>(item_off, batch + 1, off_out); note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
 
 extern "C" size_t nrb_latent_fold_workspace_bytes(int dim, int heads, int dim_head, int num_latents) {
   return fold_ws(nullptr, dim, heads, dim_head, num_latents).bytes;

@@ -52,17 +52,7 @@ class FinalAttention(nn.Module):
             w = _final_attention_weights(self, dtype, dev)
             # the MLPs act on each history slot independently (modeling_utils.py:218-222)
             x, e = ops.final_attention_rows(rows, w, dtype)
-            valid = (attention_mask.to(dev) != 0)
-            lens = valid.sum(dim=1, dtype=torch.int64)
-            off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-            off[1:] = torch.cumsum(lens, 0)
-            idx = torch.nonzero(valid.reshape(-1), as_tuple=False).reshape(-1).to(torch.int32).contiguous()
-            if idx.numel() == 0:
-                idx = torch.zeros(1, dtype=torch.int32, device=dev)
-            zeros = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-            none_idx = torch.zeros(1, dtype=torch.int32, device=dev)
-            user, _, _ = ops.score_rank(_lib.POOL_FINAL_ATTENTION, x, e, x, idx, off, none_idx, zeros, 0,
-                                        want_user=True, want_ranks=False)
+            user = ops.pool_masked_rows(x, e, attention_mask)
         return user if in_dev.type == "cuda" else user.to(in_dev)
 
 

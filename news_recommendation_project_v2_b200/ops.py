@@ -97,6 +97,34 @@ def gather_collate(table: torch.Tensor, idx: torch.Tensor, offsets: torch.Tensor
     return emb, mask
 
 
+def mask_to_csr(mask: torch.Tensor):
+    """attention_mask [B, S] (any dtype, 0 = padded) -> (idx int32 [B*S] of valid flat slots, off int64 [B+1]) on the
+    device (nrb_mask_to_csr); no host synchronisation, entries of idx beyond off[B] are unspecified."""
+    dev = require_device(mask.device)
+    if mask.dim() != 2:
+        raise _lib.NrbError("attention_mask must be [batch, seq]")
+    m = mask if mask.dtype == torch.int32 and mask.is_contiguous() else (mask != 0).to(torch.int32).contiguous()
+    B, S = m.shape
+    idx = torch.empty(max(B * S, 1), dtype=torch.int32, device=dev)
+    off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(2 * B + 2, dtype=torch.int32, device=dev)
+    check(load().nrb_mask_to_csr(ptr(m), B, S, ptr(idx), ptr(off), ptr(ws), stream_ptr()), "nrb_mask_to_csr")
+    return idx, off
+
+
+def pool_masked_rows(x: torch.Tensor, e: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    """exp-weighted masked pooling of per-slot rows x, e [B*S, d] (FinalAttention / NewAttention forward,
+    modeling_utils.py:224-228): fp32 [B, d]."""
+    dev = x.device
+    idx, off = mask_to_csr(attention_mask.to(dev))
+    B = off.numel() - 1
+    zeros = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    none_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    user, _, _ = score_rank(_lib.POOL_FINAL_ATTENTION, x, e, x, idx, off, none_idx, zeros, 0, want_user=True,
+                            want_ranks=False)
+    return user
+
+
 def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tensor], cand: torch.Tensor,
                hist_idx: torch.Tensor, hist_off: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
                n_cand_total: int, want_user: bool = False, want_ranks: bool = True,
