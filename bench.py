@@ -935,47 +935,63 @@ def leg_cfg2(dev):
 
 
 def leg_fp32(dev, model_bf16, table_host, hist_idx, h_off, cand_idx, c_off, n_imp, n_c):
-    """The rank-exact path (fp32 tables, FFMA row transform = the reference's own arithmetic) on the headline
-    workload: the number that goes with the bit-exact-rank evidence of tests/test_gpu_api.py."""
+    """The rank-exact path (fp32 tables) on the headline workload, the number that goes with the bit-exact-rank
+    evidence of tests/test_gpu_api.py: "fp32" = FFMA row transform (the reference's own arithmetic); "fp32x3" = the
+    same tables with the row transform on the tensor cores as split-bf16 GEMMs (hi/lo operand pairs, three products
+    accumulated in fp32), held to the same 1e-5 score bar by the same tests."""
     from news_recommendation_project_v2_b200 import ops
     from news_recommendation_project_v2_b200.engine import ScoringEngine
     from news_recommendation_project_v2_b200.modeling_utils import FinalAttention
 
-    m32 = FinalAttention(DIM, HIDDEN, precision="fp32").eval()
-    m32.load_state_dict(model_bf16.state_dict())
-    eng = ScoringEngine(table_host, m32.to(dev), precision="fp32", device=dev)
-    scores = torch.empty(n_c, dtype=torch.float32, device=dev)
-    ranks = torch.empty(n_c, dtype=torch.int32, device=dev)
-    flag = ops.new_err_flag(dev)
-    evs = [(_ev(), _ev(), _ev()) for _ in range(3)]
-
-    def step(e=None):
-        if e:
-            e[0].record()
-        eng.prepare_user_encoder(eng.cand)
-        if e:
-            e[1].record()
-        eng.score_device(hist_idx, h_off, cand_idx, c_off, n_c, want_ranks=True, err_flag=flag, out_scores=scores,
-                         out_ranks=ranks)
-        if e:
-            e[2].record()
-
-    step()
-    torch.cuda.synchronize()
-    for e in evs:
-        step(e)
-    torch.cuda.synchronize()
-    tr = float(np.mean([a.elapsed_time(b) for a, b, _ in evs]))
-    sc = float(np.mean([b.elapsed_time(c) for _, b, c in evs]))
     n_h = int(h_off[-1])
     alg = (2 * n_h + n_c) * DIM * 4 + 4 * (n_h + n_c) + 8 * n_c
-    res = {"value": round(n_imp / ((tr + sc) * 1e-3), 1), "unit": UNIT, "ms_per_step": round(tr + sc, 3),
-           "row_transform_ms": round(tr, 3), "row_transform_tflops_ffma": round(N_ROWS * 67.1e6 / (tr * 1e-3) / 1e12, 1),
-           "score_rank_ms": round(sc, 3), "score_rank_gbs": round(alg / (sc * 1e-3) / 1e9, 1),
-           "what": "fp32 tables + FFMA (gemm_simt) transform: scores within 1e-5 of the reference, ranks bit-exact "
-                   "wherever the reference's score gaps exceed that (test_gpu_api.py)"}
-    del eng
-    torch.cuda.empty_cache()
+    res, ref_scores = {}, None
+    for precision in ("fp32", "fp32x3"):
+        m32 = FinalAttention(DIM, HIDDEN, precision=precision).eval()
+        m32.load_state_dict(model_bf16.state_dict())
+        eng = ScoringEngine(table_host, m32.to(dev), precision=precision, device=dev)
+        scores = torch.empty(n_c, dtype=torch.float32, device=dev)
+        ranks = torch.empty(n_c, dtype=torch.int32, device=dev)
+        flag = ops.new_err_flag(dev)
+        evs = [(_ev(), _ev(), _ev()) for _ in range(3)]
+
+        def step(e=None):
+            if e:
+                e[0].record()
+            eng.prepare_user_encoder(eng.cand)
+            if e:
+                e[1].record()
+            eng.score_device(hist_idx, h_off, cand_idx, c_off, n_c, want_ranks=True, err_flag=flag, out_scores=scores,
+                             out_ranks=ranks)
+            if e:
+                e[2].record()
+
+        step()
+        torch.cuda.synchronize()
+        for e in evs:
+            step(e)
+        torch.cuda.synchronize()
+        tr = float(np.mean([a.elapsed_time(b) for a, b, _ in evs]))
+        sc = float(np.mean([b.elapsed_time(c) for _, b, c in evs]))
+        r = {"value": round(n_imp / ((tr + sc) * 1e-3), 1), "unit": UNIT, "ms_per_step": round(tr + sc, 3),
+             "row_transform_ms": round(tr, 3), "score_rank_ms": round(sc, 3),
+             "score_rank_gbs": round(alg / (sc * 1e-3) / 1e9, 1)}
+        if precision == "fp32":
+            r["row_transform_tflops_ffma"] = round(N_ROWS * 67.1e6 / (tr * 1e-3) / 1e12, 1)
+            ref_scores, ref_ranks = scores.clone(), ranks.clone()
+            res.update(r)
+            res["what"] = ("fp32 tables + FFMA (gemm_simt) transform: scores within 1e-5 of the reference, ranks "
+                           "bit-exact wherever the reference's score gaps exceed that (test_gpu_api.py)")
+        else:
+            r["row_transform_tflops_tensor_executed"] = round(3 * N_ROWS * 67.1e6 / (tr * 1e-3) / 1e12, 1)
+            r["max_abs_score_diff_vs_fp32"] = float((scores - ref_scores).abs().max())
+            r["impressions_with_rank_diff_vs_fp32"] = int(torch.unique(torch.bucketize(
+                torch.nonzero(ranks != ref_ranks).flatten(), c_off[1:], right=True)).numel())
+            r["what"] = ("fp32 tables, row transform as split-bf16 tcgen05 GEMMs (K' = 3K: a_hi w_hi + a_hi w_lo + "
+                         "a_lo w_hi accumulated in fp32)")
+            res["fp32x3"] = r
+        del eng
+        torch.cuda.empty_cache()
     return res
 
 

@@ -169,6 +169,20 @@ int nrb_final_attention_rows(int precision, int out_dtype, const void* table, in
                              const void* w5, void* x_out, void* e_out, int64_t out_stride,
                              void* workspace, size_t workspace_bytes, nrb_stream_t stream);
 
+/* Split-bf16 tensor-core variant for fp32 tables (the rank-exact path): with hi = bf16(v), lo = bf16(v - hi),
+ * nrb_split_rows writes [hi | hi | lo] (role 0, activations) or [hi | lo | hi] (role 1, weights) as bf16 rows of
+ * 3*dim columns, so that ONE tcgen05 GEMM over K' = 3K accumulates a_hi w_hi + a_hi w_lo + a_lo w_hi in fp32
+ * (~2^-17 relative per operand instead of bf16's 2^-9).  nrb_final_attention_rows_split runs the five Linear layers
+ * of modeling_utils.py:218-224 that way: fp32 table in, fp32 x / exp(logit) out, weights pre-split with role 1. */
+int nrb_split_rows(const float* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t n_rows, int dim,
+                   int role, nrb_stream_t stream);
+size_t nrb_final_attention_rows_split_workspace_bytes(int64_t n_rows, int dim, int hidden);
+int nrb_final_attention_rows_split(const float* table, int64_t table_stride, int64_t n_rows, int dim, int hidden,
+                                   const void* w1s, const float* b1, const void* w2s, const float* b2,
+                                   const void* w3s, const float* b3, const void* w4s, const float* b4,
+                                   const void* w5s, float* x_out, float* e_out, int64_t out_stride,
+                                   void* workspace, size_t workspace_bytes, nrb_stream_t stream);
+
 /* ---- Stage A: latent-attention pooling ---------------------------------------------------
  * replaces latent_attention.py:134-171 LatentAttentionModel.forward.
  *

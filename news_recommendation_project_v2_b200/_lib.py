@@ -68,6 +68,10 @@ PROTOTYPES = {
                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64,
                                         _c_void_p, _sz, _c_void_p]),
+    "nrb_split_rows": (_i32, [_c_void_p, _i64, _c_void_p, _i64, _i64, _i32, _i32, _c_void_p]),
+    "nrb_final_attention_rows_split_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "nrb_final_attention_rows_split": (_i32, [_c_void_p, _i64, _i64, _i32, _i32] + [_c_void_p] * 9 +
+                                       [_c_void_p, _c_void_p, _i64, _c_void_p, _sz, _c_void_p]),
     "nrb_latent_fold_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "nrb_latent_fold": (_i32, [_i32, _i32, _i32, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _sz, _c_void_p]),

@@ -35,6 +35,9 @@ TORCH_DTYPE = torch.float32  # config.py:39
 # Arithmetic of the CUDA hot path:
 #   "bf16": bf16 tables / weights, tcgen05 tensor cores with fp32 accumulation (throughput path)
 #   "fp32": fp32 tables / weights, FFMA accumulation (the reference's own arithmetic; parity path)
+#   "fp32x3": fp32 tables; the FinalAttention row transform runs on the tensor cores as split-bf16 GEMMs
+#             (hi/lo operand pairs, three products accumulated in fp32: ~2^-17 relative per operand); every other
+#             dense op of that mode uses the fp32 FFMA kernels
 PRECISION = os.environ.get("NRB200_PRECISION", "bf16")
 
 # Tokens processed per latent-attention chunk (bounds the workspace: ~23 KB / token in bf16 at d=768, L=512, i.e.
@@ -51,6 +54,10 @@ def precision_dtype(precision: str | torch.dtype | None = None) -> torch.dtype:
         raise ValueError(f"unsupported precision {p}")
     if p in ("bf16", "bfloat16"):
         return torch.bfloat16
-    if p in ("fp32", "float32"):
+    if p in ("fp32", "float32", "fp32x3"):
         return torch.float32
-    raise ValueError(f"unsupported precision {p!r} (use 'bf16' or 'fp32')")
+    raise ValueError(f"unsupported precision {p!r} (use 'bf16', 'fp32' or 'fp32x3')")
+
+
+def precision_is_split(precision: str | torch.dtype | None = None) -> bool:
+    return (PRECISION if precision is None else precision) == "fp32x3"

@@ -229,6 +229,44 @@ convert_f32_bf16_vec_kernel(const float* src, int64_t lds, __nv_bfloat16* dst, i
   }
 }
 
+// fp32 -> three bf16 column blocks for the split-bf16 tensor-core path: with hi = bf16(v), lo = bf16(v - hi)
+//   role 0 (activation rows):  [ hi | hi | lo ]        role 1 (weight rows):  [ hi | lo | hi ]
+// so that ONE bf16 GEMM over K' = 3K accumulates a_hi w_hi + a_hi w_lo + a_lo w_hi in fp32 (the dropped a_lo w_lo
+// term and the 16-bit truncation of each operand are ~2^-17 relative).
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* src, int64_t lds, __nv_bfloat16* dst, int64_t ldd, int64_t rows, int k4, int role) {
+  const int64_t total = rows * k4;
+  const int K = k4 * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k4;
+    const int c = (int)(i - r * k4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hi[q] = __bfloat162float(__float2bfloat16_rn(f[q]));
+      lo[q] = f[q] - hi[q];  // exact in fp32
+    }
+    const uint2 H = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+    const uint2 L = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+    __nv_bfloat16* d = dst + r * ldd + c;
+    *reinterpret_cast<uint2*>(d) = H;
+    *reinterpret_cast<uint2*>(d + K) = role == 0 ? H : L;
+    *reinterpret_cast<uint2*>(d + 2 * K) = role == 0 ? L : H;
+  }
+}
+
+int split_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int K, int role, cudaStream_t st) {
+  if (rows <= 0) return NRB_OK;
+  const int64_t want = (rows * (K / 4) + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count_cached() * 16);
+  split_rows_kernel<<<grid, 256, 0, st>>>(src, lds, (__nv_bfloat16*)dst, ldd, rows, K / 4, role);
+  note_launch();
+  NRB_CUDA_CHECK(cudaGetLastError());
+  return NRB_OK;
+}
+
 int convert_rows(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows,
                  int cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return NRB_OK;
@@ -335,6 +373,78 @@ extern "C" int nrb_linear(int precision, int epilogue, int out_dtype, const void
   NRB_REQUIRE(a && w && y, "nrb_linear: null pointer");
   return linear(precision, epilogue, out_dtype, a, lda, w, ldw, bias, res, ldres, y, ldy, M, nullptr, N, K,
                 as_stream(stream), group, group_valid);
+}
+
+extern "C" int nrb_split_rows(const float* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t n_rows,
+                              int dim, int role, nrb_stream_t stream) {
+  NRB_REQUIRE(n_rows >= 0 && dim > 0 && dim % 4 == 0, "nrb_split_rows: dim must be a positive multiple of 4");
+  NRB_REQUIRE(role == 0 || role == 1, "nrb_split_rows: role must be 0 (activations) or 1 (weights)");
+  if (n_rows == 0) return NRB_OK;
+  NRB_REQUIRE(src && dst, "nrb_split_rows: null pointer");
+  NRB_REQUIRE(src_stride % 4 == 0 && dst_stride % 4 == 0 && dst_stride >= 3 * (int64_t)dim &&
+                  (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+              "nrb_split_rows: alignment / stride");
+  return split_rows(src, src_stride, dst, dst_stride, n_rows, dim, role, as_stream(stream));
+}
+
+// split-bf16 variant of the FinalAttention row transform: fp32 table in, fp32 x / exp(logit) out, every Linear as ONE
+// tcgen05 GEMM over K' = 3K on [hi|hi|lo] x [hi|lo|hi] operands (weights pre-split by nrb_split_rows, role 1)
+static size_t fa_split_ws(int64_t n_rows, int dim, int hidden, float** act, void** sp, void* base) {
+  const int64_t chunk = std::min<int64_t>(n_rows, kFaChunkRows);
+  const int wide = std::max(dim, hidden);
+  Workspace ws(base, (size_t)-1);
+  float* a = (float*)ws.take((size_t)chunk * wide * 4);
+  void* s3 = ws.take((size_t)chunk * 3 * wide * 2);
+  if (act) *act = a;
+  if (sp) *sp = s3;
+  return ws.used + 256;
+}
+
+extern "C" size_t nrb_final_attention_rows_split_workspace_bytes(int64_t n_rows, int dim, int hidden) {
+  return fa_split_ws(n_rows, dim, hidden, nullptr, nullptr, nullptr);
+}
+
+extern "C" int nrb_final_attention_rows_split(const float* table, int64_t table_stride, int64_t n_rows, int dim,
+                                              int hidden, const void* w1s, const float* b1, const void* w2s,
+                                              const float* b2, const void* w3s, const float* b3, const void* w4s,
+                                              const float* b4, const void* w5s, float* x_out, float* e_out,
+                                              int64_t out_stride, void* workspace, size_t workspace_bytes,
+                                              nrb_stream_t stream) {
+  NRB_REQUIRE(n_rows > 0 && dim > 0 && hidden > 0 && dim % 64 == 0 && hidden % 64 == 0,
+              "nrb_final_attention_rows_split: dim and hidden must be multiples of 64");
+  NRB_REQUIRE(table && w1s && b1 && w2s && b2 && w3s && b3 && w4s && b4 && w5s && x_out && e_out && workspace,
+              "nrb_final_attention_rows_split: null pointer");
+  float* act;
+  void* sp;
+  if (workspace_bytes < fa_split_ws(n_rows, dim, hidden, &act, &sp, workspace)) {
+    set_error("nrb_final_attention_rows_split: workspace too small");
+    return NRB_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int64_t chunk = std::min<int64_t>(n_rows, kFaChunkRows);
+  const int d3 = 3 * dim, h3 = 3 * hidden;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n_rows - r0);
+    float* xo = x_out + r0 * out_stride;
+    float* eo = e_out + r0 * out_stride;
+    int rc;
+#define NRB_SPLIT_LINEAR(SRC, LDS, KIN, W, BIAS, EPI, DST, LDD, NOUT)                                                  \
+  if ((rc = split_rows(SRC, LDS, sp, 3 * (KIN), m, KIN, 0, st)) != NRB_OK) return rc;                                  \
+  if ((rc = gemm_bf16_tc(EPI, NRB_F32, sp, 3 * (KIN), W, 3 * (KIN), BIAS, nullptr, 0, DST, LDD, m, nullptr, NOUT,      \
+                         3 * (KIN), 0, 0, st)) != NRB_OK)                                                              \
+    return rc;
+    // x = W3 relu(W2 relu(W1 e + b1) + b2) + b3          (modeling_utils.py:218-220)
+    NRB_SPLIT_LINEAR(table + r0 * table_stride, table_stride, dim, w1s, b1, NRB_EPI_RELU, act, hidden, hidden)
+    NRB_SPLIT_LINEAR(act, hidden, hidden, w2s, b2, NRB_EPI_RELU, act, hidden, hidden)
+    NRB_SPLIT_LINEAR(act, hidden, hidden, w3s, b3, NRB_EPI_NONE, xo, out_stride, dim)
+    // elog = exp(W5 relu(W4 x + b4))                        (modeling_utils.py:221-224)
+    NRB_SPLIT_LINEAR(xo, out_stride, dim, w4s, b4, NRB_EPI_RELU, act, hidden, hidden)
+    NRB_SPLIT_LINEAR(act, hidden, hidden, w5s, nullptr, NRB_EPI_EXP, eo, out_stride, dim)
+#undef NRB_SPLIT_LINEAR
+    (void)d3;
+    (void)h3;
+  }
+  return NRB_OK;
 }
 
 extern "C" size_t nrb_final_attention_rows_workspace_bytes(int precision, int64_t n_rows, int dim, int hidden) {

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .config import LATENT_MAX_TOKENS, precision_dtype
+from .config import LATENT_MAX_TOKENS, precision_dtype, precision_is_split
 from .synthetic import csr_offsets
 
 _table_cache: "dict[tuple, tuple[weakref.ref, torch.Tensor]]" = {}
@@ -66,6 +66,12 @@ def _offsets(lengths, device) -> tuple[torch.Tensor, int]:
     return torch.from_numpy(off).to(device), int(off[-1])
 
 
+def _final_attention_weights_split(model, device) -> dict:
+    """fp32 weights -> [hi|lo|hi] bf16 operands of the split-bf16 tensor-core GEMMs (nrb_split_rows role 1)."""
+    w32 = _final_attention_weights(model, torch.float32, device)
+    return {k: (ops.split_rows(v, 1) if k.endswith("weight") else v) for k, v in w32.items()}
+
+
 def _final_attention_weights(model, dtype: torch.dtype, device) -> dict:
     sd = model.state_dict()
     need = [f"linear{i}.weight" for i in range(1, 6)] + [f"linear{i}.bias" for i in range(1, 5)]
@@ -89,6 +95,7 @@ class ScoringEngine:
 
         self.device = _lib.require_device(device)
         self.dtype = precision_dtype(precision)
+        self.split = precision_is_split(precision)
         self.model = model
         self.n_rows, self.dim = news_embeddings.shape
         self._streams = None
@@ -96,7 +103,7 @@ class ScoringEngine:
             from .attention import NewAttention
             streamed = (not cache_table and not news_embeddings.is_cuda and query_news_embeddings is None
                         and not isinstance(model, (LatentAttentionModel, NewAttention))
-                        and news_embeddings.dtype == torch.float32)
+                        and news_embeddings.dtype == torch.float32 and not self.split)
             if streamed:
                 self._upload_and_transform_streamed(news_embeddings)
                 return
@@ -234,9 +241,13 @@ class ScoringEngine:
             # kernel-ready weights stay resident until a parameter changes (trainers update them per epoch)
             fp = _model_fingerprint(self.model)
             if getattr(self, "_fa_weights_key", None) != fp:
-                self._fa_weights = _final_attention_weights(self.model, self.dtype, self.device)
+                self._fa_weights = (_final_attention_weights_split(self.model, self.device) if self.split else
+                                    _final_attention_weights(self.model, self.dtype, self.device))
                 self._fa_weights_key = fp
-            self.hist_x, self.hist_e = ops.final_attention_rows(hist_src, self._fa_weights, self.dtype)
+            if self.split:
+                self.hist_x, self.hist_e = ops.final_attention_rows_split(hist_src, self._fa_weights)
+            else:
+                self.hist_x, self.hist_e = ops.final_attention_rows(hist_src, self._fa_weights, self.dtype)
             self.pool_mode = _lib.POOL_FINAL_ATTENTION
 
     # -- fused gather + pool + cosine + rank ---------------------------------------------------------
@@ -302,7 +313,7 @@ def cached_engine(news_embeddings: torch.Tensor, model: torch.nn.Module,
     q = query_news_embeddings
     key = (id(news_embeddings), news_embeddings.data_ptr(), news_embeddings._version,
            None if q is None else (id(q), q.data_ptr(), q._version), id(model), _model_fingerprint(model),
-           str(precision_dtype(precision)))
+           str(precision_dtype(precision)), precision_is_split(precision))
     hit = _engine_cache.get(key)
     if hit is not None:
         # id / data_ptr / _version can all repeat after the table is freed (or be untouched by a numpy-side

@@ -229,6 +229,43 @@ def final_attention_rows(table: torch.Tensor, weights: dict, out_dtype: torch.dt
     return x, e
 
 
+def split_rows(src: torch.Tensor, role: int) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 [rows, 3K]: [hi|hi|lo] (role 0, activations) or [hi|lo|hi] (role 1, weights)."""
+    dev = require_device(src.device)
+    _dev(src, "src", torch.float32)
+    rows, K = src.shape
+    out = torch.empty(rows, 3 * K, dtype=torch.bfloat16, device=dev)
+    check(load().nrb_split_rows(ptr(src), src.stride(0), ptr(out), out.stride(0), rows, K, int(role), stream_ptr()),
+          "nrb_split_rows")
+    return out
+
+
+def final_attention_rows_split(table: torch.Tensor, weights: dict, x_out: Optional[torch.Tensor] = None,
+                               e_out: Optional[torch.Tensor] = None):
+    """Per-row FinalAttention transform on the tensor cores at (almost) fp32 accuracy: fp32 table, weights
+    `linear{1..5}.weight` pre-split by `split_rows(w, 1)`, fp32 biases -> fp32 (x, exp(logit)) tables."""
+    dev = require_device(table.device)
+    _dev(table, "table", torch.float32)
+    n_rows, dim = table.shape
+    hidden = weights["linear1.bias"].shape[0]
+    for i in range(1, 6):
+        _dev(weights[f"linear{i}.weight"], f"linear{i}.weight", torch.bfloat16)
+    lib = load()
+    ws_bytes = lib.nrb_final_attention_rows_split_workspace_bytes(n_rows, dim, hidden)
+    ws = _workspace(dev, ws_bytes, "fa_split")
+    x = x_out if x_out is not None else torch.empty(n_rows, dim, dtype=torch.float32, device=dev)
+    e = e_out if e_out is not None else torch.empty(n_rows, dim, dtype=torch.float32, device=dev)
+    check(lib.nrb_final_attention_rows_split(
+        ptr(table), table.stride(0), n_rows, dim, hidden,
+        ptr(weights["linear1.weight"]), ptr(weights["linear1.bias"]),
+        ptr(weights["linear2.weight"]), ptr(weights["linear2.bias"]),
+        ptr(weights["linear3.weight"]), ptr(weights["linear3.bias"]),
+        ptr(weights["linear4.weight"]), ptr(weights["linear4.bias"]),
+        ptr(weights["linear5.weight"]), ptr(x), ptr(e), x.stride(0), ptr(ws), ws.numel(), stream_ptr()),
+        "nrb_final_attention_rows_split")
+    return x, e
+
+
 @dataclass
 class FoldedLatent:
     """Device-resident, kernel-ready weights of one LatentAttentionModel."""

@@ -34,21 +34,25 @@ def _rank_mismatches(got_ranks, ref_ranks, ref_scores, cand_len, gap):
     return hard, soft
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp32x3"])
 @pytest.mark.parametrize("name", ["final_small_d768", "final_large_d1024"])
-def test_final_second_attention_score_fp32_matches_reference(golden_dir, name):
+def test_final_second_attention_score_fp32_matches_reference(golden_dir, name, precision):
     """fp32 path vs the reference's own outputs: scores 1e-5, rankings bit-exact wherever the
-    reference's adjacent score gaps exceed 1e-5, metrics equal to 4 decimals."""
+    reference's adjacent score gaps exceed 1e-5, metrics equal to 4 decimals.  "fp32x3" = the same fp32 tables with
+    the row transform on the tensor cores as split-bf16 GEMMs (three hi/lo products accumulated in fp32): held to the
+    same bars."""
     from news_recommendation_project_v2_b200.data_model_helper import (
         get_final_second_attention_score, get_final_attention_eval, get_cos_sim_scores)
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     dim, hidden, n_rows, n_imp, seed = (int(g[k]) for k in ("dim", "hidden", "n_rows", "n_imp", "seed"))
-    model = _final_model(dim, hidden, seed, "fp32")
+    model = _final_model(dim, hidden, seed, precision)
     table = syn.make_table(n_rows, dim, seed=seed + 2)
     imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand=str(g["cand"]), seed=seed + 3)
     hb = np.ones(n_imp, dtype=bool)
     out = get_final_second_attention_score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, hb, model,
-                                           precision="fp32")
+                                           precision=precision)
     assert out["scores"].dtype == np.float32 and out["scores"].shape == g["scores"].shape
+    print(f"{name} {precision}: max |score - reference| = {np.abs(out['scores'] - g['scores']).max():.3e}")
     np.testing.assert_allclose(out["scores"], g["scores"], atol=1e-5, rtol=0)
     assert out["grouped_scores"].dtype == object and len(out["grouped_scores"]) == n_imp
     ranks = np.concatenate([np.asarray(r) for r in out["grouped_scores"]])
@@ -56,9 +60,9 @@ def test_final_second_attention_score_fp32_matches_reference(golden_dir, name):
     assert hard == 0 and soft <= 2
     metrics = np.array([oracle.score_row(imp.labels[i], out["grouped_scores"][i]) for i in range(n_imp)])
     np.testing.assert_allclose(metrics.mean(0), g["metrics"].mean(0), atol=5e-5, rtol=0)
-    user = get_final_attention_eval(imp.hist_idx, imp.hist_len, table, model, precision="fp32")
+    user = get_final_attention_eval(imp.hist_idx, imp.hist_len, table, model, precision=precision)
     np.testing.assert_allclose(user.numpy(), g["user"], atol=2e-5, rtol=2e-5)
-    sc = get_cos_sim_scores(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, model, precision="fp32")
+    sc = get_cos_sim_scores(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, model, precision=precision)
     assert sc.device.type == "cpu" and np.array_equal(sc.numpy(), out["scores"])
 
 
