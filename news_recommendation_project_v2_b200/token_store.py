@@ -145,6 +145,19 @@ def convert_token_store(db_name: str, out_path: str, dtype: torch.dtype = torch.
         conn.close()
 
 
+def _clear_cuda_last_error() -> None:
+    """cudaGetLastError() in the CUDA runtime torch itself is linked against (torch exposes no binding for it): a
+    failed cudaHostRegister otherwise stays pending and is reported by the next unrelated torch call."""
+    import ctypes
+
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            ctypes.CDLL(name).cudaGetLastError()
+            return
+        except OSError:
+            continue
+
+
 class PackedTokenFile:
     """mmap view of a packed token file: `.offsets` int64 [n_items + 1], `.tokens_raw` [n_tokens, dim] (uint16 bit
     patterns for bf16), `.tokens(a, b)` -> torch view of token rows [a, b) in the file dtype."""
@@ -182,6 +195,8 @@ class PackedTokenFile:
             self._registered = ok
         except Exception:
             self._registered = False
+        if not self._registered:
+            _clear_cuda_last_error()  # a refused registration must not surface later as somebody else's error
         return self._registered
 
     def unregister(self) -> None:
