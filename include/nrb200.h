@@ -283,6 +283,9 @@ typedef struct nrb_push_seg {
 } nrb_push_seg;
 int nrb_push_attach(const nrb_push_seg* segs, int n_segs, int spread);
 int nrb_push_flush(nrb_stream_t stream);
+/* drop pending segments without sending them (error paths: nothing stale may ride in a later, unrelated GEMM).
+ * Pending segments are per host thread AND per device: launches on another device never carry them. */
+void nrb_push_cancel(void);
 
 /* ---- behaviour log -> CSR index builder (host; the step in front of the hot path) ------------------
  * replaces data_utils.py:168-232 split_impressions_and_history.  `impressions` / `history` are

@@ -61,12 +61,16 @@ struct PendingPush {
   int64_t done[kMaxPushSegs];
   int64_t share[kMaxPushSegs];
   int n_seg = 0;
+  int device = -1;  // only GEMM launches on the device the segments live on may carry them
 };
 static thread_local PendingPush g_pending;
 
 static void cut_share(PushJob* job, bool everything) {
   job->n_seg = 0;
   PendingPush& q = g_pending;
+  if (q.n_seg == 0) return;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != q.device) return;  // another device's launch: not its rows
   bool left = false;
   for (int i = 0; i < q.n_seg; ++i) {
     const int64_t remain = q.seg[i].n_rows - q.done[i];
@@ -124,8 +128,11 @@ extern "C" int nrb_push_attach(const nrb_push_seg* segs, int n_segs, int spread)
     g_pending.share[i] = (u.n_rows + spread - 1) / spread;
   }
   g_pending.n_seg = n_segs;
+  NRB_CUDA_CHECK(cudaGetDevice(&g_pending.device));
   return NRB_OK;
 }
+
+extern "C" void nrb_push_cancel(void) { g_pending.n_seg = 0; }
 
 extern "C" int nrb_push_flush(nrb_stream_t stream) {
   PushJob job;

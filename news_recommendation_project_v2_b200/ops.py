@@ -429,6 +429,11 @@ def push_attach(segments: list, spread: int) -> None:
     check(load().nrb_push_attach(arr, len(segments), int(spread)), "nrb_push_attach")
 
 
+def push_cancel() -> None:
+    """Drop pending all-gather segments without sending them (error paths)."""
+    load().nrb_push_cancel()
+
+
 def push_flush() -> None:
     """Send what no GEMM picked up with the store-only multicast kernel (nrb_push_flush)."""
     check(load().nrb_push_flush(stream_ptr()), "nrb_push_flush")

@@ -203,6 +203,13 @@ class ShardedTableEngine(ScoringEngine):
         CTAs that compute chunk i+1; the last chunk leaves through the store-only flush kernel."""
         r0, r1 = self._bounds
         d, dev, mc = self.dim, self.device, self._mc
+        try:
+            self._build_nvls_chunks(local_rows, fw, w, r0, r1, d, dev, mc)
+        except BaseException:
+            ops.push_cancel()  # nothing stale may ride in a later, unrelated GEMM launch
+            raise
+
+    def _build_nvls_chunks(self, local_rows, fw, w, r0, r1, d, dev, mc) -> None:
         prev = None
         for c0 in range(0, r1 - r0, self.chunk_rows):
             c1 = min(r1 - r0, c0 + self.chunk_rows)
