@@ -301,6 +301,12 @@ int nrb_csr_export(void* handle, int32_t* hist_idx, int32_t* hist_owner, int32_t
 int64_t nrb_csr_news_ids(void* handle, char* out, int64_t cap);
 void nrb_csr_free(void* handle);
 
+/* ---- host staging for the packed token file (the data format in front of Stage A) -------------------------
+ * (replaces the per-item sqlite read + torch.load + pad-to-batch-max of data_utils.py:878-933, 753-781: a chunk of
+ * items is one contiguous byte range of the mmap'd file.)  memcpy of `n_bytes` HOST bytes split over `n_threads`
+ * worker threads (page cache -> pinned staging buffer); blocks until done. */
+int nrb_host_copy(void* dst_host, const void* src_host, int64_t n_bytes, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

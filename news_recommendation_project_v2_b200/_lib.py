@@ -83,6 +83,7 @@ PROTOTYPES = {
     "nrb_push_attach": (_i32, [C.POINTER(PushSeg), _i32, _i32]),
     "nrb_push_flush": (_i32, [_c_void_p]),
     "nrb_push_cancel": (None, []),
+    "nrb_host_copy": (_i32, [_c_void_p, _c_void_p, _i64, _i32]),
     "nrb_csr_build": (_c_void_p, [C.c_char_p, _i64, C.c_char_p, _i64, _i64]),
     "nrb_csr_sizes": (_i32, [_c_void_p, C.POINTER(_i64)]),
     "nrb_csr_export": (_i32, [_c_void_p] * 8),

@@ -18,7 +18,6 @@ import io
 import os
 import sqlite3
 import struct
-from concurrent.futures import ThreadPoolExecutor
 from typing import Iterable, Optional
 
 import numpy as np
@@ -246,7 +245,6 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
         out = torch.empty(tf.n_items, d, dtype=torch.float32).pin_memory()
     with torch.cuda.device(dev):
         pinned = [torch.empty(chunk_tokens, d, dtype=tdt).pin_memory() for _ in range(2)]
-        pinned_np = [p.numpy().view(npdt) for p in pinned]
         dbuf = [torch.empty(chunk_tokens, d, dtype=tdt, device=dev) for _ in range(2)]
         obuf = [None, None]
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -254,7 +252,7 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
         h2d_done = [None, None]
         compute_done = [None, None]
         d2h_done = [None, None]
-        pool = ThreadPoolExecutor(max_workers=max(1, copy_threads))
+        lib = _lib.load()
 
         direct = bool(getattr(tf, "_registered", False))  # mapped section page-locked: DMA straight from the mapping
 
@@ -281,9 +279,10 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
             if h2d_done[b] is not None:
                 h2d_done[b].synchronize()  # the pinned buffer is free once its previous upload has finished
             if n:
-                cuts = np.linspace(0, n, num=min(copy_threads, max(1, n // 4096)) + 1, dtype=np.int64)
-                list(pool.map(lambda ab: np.copyto(pinned_np[b][ab[0]:ab[1]], tf.tokens_raw[t0 + ab[0]:t0 + ab[1]]),
-                              zip(cuts[:-1], cuts[1:])))
+                # page cache -> pinned staging buffer: native multi-threaded memcpy (no GIL, whole pages per thread)
+                src = tf.tokens_raw[t0:t1]
+                _lib.check(lib.nrb_host_copy(pinned[b].data_ptr(), src.ctypes.data, src.nbytes, copy_threads),
+                           "nrb_host_copy")
             if compute_done[b] is not None:
                 s_in.wait_event(compute_done[b])  # the device buffer is free once chunk k-2 has been pooled
             with torch.cuda.stream(s_in):
@@ -318,5 +317,5 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
             s_out.synchronize()
             cur.synchronize()
         finally:
-            pool.shutdown(wait=True)
+            torch.cuda.current_stream().synchronize()
     return out
