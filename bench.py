@@ -1128,10 +1128,48 @@ def run_reference_gpu(args):
         _quiet(run, table, imp)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t) / steps
+    stage_a = _reference_stage_a_gpu()
     print(json.dumps({"impl": "reference-gpu", "value": round(n / dt, 1), "unit": UNIT, "ms_per_step": round(dt * 1e3, 1),
+                      "stage_a": stage_a,
                       "sample": "%d cfg-4-shaped impressions per step, fp32, %s with DEVICE=cuda (torch %s on %s), user-"
                                 "encoder batch 512" % (n, what, torch.__version__, torch.cuda.get_device_name(0)),
                       "steps": steps}), flush=True)
+
+
+def _reference_stage_a_gpu():
+    """The reference's own LatentAttentionModel (latent_attention.py:134-171) with DEVICE=cuda on this GPU, cfg-2
+    shape (seq 64, d 768, 512 latents), fp32 like the reference's TORCH_DTYPE and under bf16 autocast."""
+    try:
+        from oracle import ref_harness
+
+        ref = ref_harness.load_reference(batch_size=512, device="cuda")
+        d, L, S, B, reps = 768, 512, 64, 256, 8
+        model = ref_harness.make_reference_latent_model(ref, d, L, seed=1234)
+        model.load_state_dict(syn.make_latent_state_dict(d, L, seed=1234))
+        model = model.to("cuda").eval()
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        x = torch.randn(B, S, d, generator=g, device="cuda")
+        lens = torch.randint(8, S + 1, (B,), generator=g, device="cuda")
+        mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).to(torch.int32)
+        out = {}
+        for name, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            def run():
+                with torch.no_grad():
+                    if ctx is None:
+                        return model(x, mask)
+                    with ctx:
+                        return model(x, mask)
+            _quiet(run)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(reps):
+                _quiet(run)
+            torch.cuda.synchronize()
+            out[name + "_news_per_s"] = round(B * reps / (time.perf_counter() - t), 1)
+        out["sample"] = "%d x %d items x %d tokens, d=%d, L=%d, reference module on cuda" % (reps, B, S, d, L)
+        return out
+    except Exception as exc:  # pragma: no cover - reported, not hidden
+        return {"unavailable": repr(exc)[:300]}
 
 
 def reference_gpu_subprocess():
