@@ -11,3 +11,4 @@ run() {  # name, extra args
 run p2p "--gather p2p"
 run dma "--gather dma"
 run nccl "--gather nccl"
+run nvls "--gather nvls"
