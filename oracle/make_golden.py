@@ -54,7 +54,7 @@ def golden_latent(ref, name, dim, L, B, S, seed):
     print(name, pooled.shape, float(pooled.norm(dim=-1).mean()))
 
 
-def golden_final(ref, name, dim, hidden, n_rows, n_imp, cand, seed):
+def golden_final(ref, name, dim, hidden, n_rows, n_imp, cand, seed, users_kept=None):
     model = ref_harness.make_reference_final_attention(ref, dim, hidden, seed=seed)
     sd = syn.make_final_attention_state_dict(dim, hidden, seed=seed)
     model.load_state_dict(sd, strict=True)
@@ -73,7 +73,8 @@ def golden_final(ref, name, dim, hidden, n_rows, n_imp, cand, seed):
         os.path.join(GOLD, f"{name}.npz"),
         dim=dim, hidden=hidden, n_rows=n_rows, n_imp=n_imp, cand=cand, seed=seed,
         sd_sha256=sd_digest(sd), scores=np.asarray(out["scores"], dtype=np.float32),
-        ranks=ranks, user=user.numpy(), metrics=metrics,
+        ranks=ranks if users_kept is None else ranks.astype(np.int16),  # medium fixture: compact storage
+        user=user.numpy() if users_kept is None else user.numpy()[:users_kept], metrics=metrics,
     )
     print(name, "scores", out["scores"].shape, "mean metrics", metrics.mean(axis=0))
 
@@ -196,6 +197,8 @@ def main():
     if only:
         if "latent_cfg5_d1024_L1024" in only:
             golden_latent(ref, "latent_cfg5_d1024_L1024", 1024, 1024, 4, 24, seed=555)
+        if "final_medium_d1024" in only:
+            golden_final(ref, "final_medium_d1024", 1024, 4096, 20000, 1024, "large", seed=7, users_kept=32)
         if "latent_user_cfg5_d1024_L1024_H200" in only:
             golden_latent_user_encoder(ref, "latent_user_cfg5_d1024_L1024_H200", 1024, 1024, 3000, 20, 200, seed=777)
         return
@@ -206,6 +209,8 @@ def main():
     golden_latent(ref, "latent_default_d1024_L64", 1024, 64, 4, 16, seed=4321)
     golden_final(ref, "final_small_d768", 768, 4096, 4096, 64, "small", seed=1234)
     golden_final(ref, "final_large_d1024", 1024, 4096, 2048, 48, "large", seed=99)
+    # 1,024 impressions / 37 k candidates through the unmodified reference: the rank-exactness fixture
+    golden_final(ref, "final_medium_d1024", 1024, 4096, 20000, 1024, "large", seed=7, users_kept=32)
     # BASELINE configs[4] shapes (d=1024, 1024 latents, histories up to 200)
     golden_latent(ref, "latent_cfg5_d1024_L1024", 1024, 1024, 4, 24, seed=555)
     golden_latent_user_encoder(ref, "latent_user_cfg5_d1024_L1024_H200", 1024, 1024, 3000, 20, 200, seed=777)

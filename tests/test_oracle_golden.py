@@ -80,6 +80,31 @@ def test_final_attention_score_rank_matches_reference(golden_dir, name):
     np.testing.assert_allclose(m, g["metrics"], atol=1e-12, rtol=0)
 
 
+def test_final_attention_medium_fixture_matches_reference(golden_dir):
+    """1,024 impressions / 39 k candidates through the unmodified reference: oracle scores within 2e-6, dense ranks
+    from the reference's own score bits bit-exact, metrics to 1e-12."""
+    g = _load(golden_dir, "final_medium_d1024")
+    dim, hidden, n_rows, n_imp, seed = (int(g[k]) for k in ("dim", "hidden", "n_rows", "n_imp", "seed"))
+    sd = syn.make_final_attention_state_dict(dim, hidden, seed=seed)
+    assert _digest(sd) == str(g["sd_sha256"])
+    table = syn.make_table(n_rows, dim, seed=seed + 2)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand=str(g["cand"]), seed=seed + 3)
+    ref_ranks = g["ranks"].astype(np.float64)
+    assert np.array_equal(np.concatenate(oracle.rank_group_preds(g["scores"], imp.cand_len)), ref_ranks)
+    grouped = oracle.group_items(ref_ranks, imp.cand_len)
+    m = np.array([oracle.score_row(imp.labels[i], grouped[i]) for i in range(n_imp)])
+    # exactly tied scores with different labels depend on numpy's unstable argsort (DESIGN section 1): AUC always
+    tied = np.array([len(np.unique(r)) < len(r) for r in grouped])
+    np.testing.assert_allclose(m[~tied], g["metrics"][~tied], atol=1e-12, rtol=0)
+    np.testing.assert_allclose(m[:, 0], g["metrics"][:, 0], atol=1e-12, rtol=0)
+    sub = slice(0, 64)  # the fp64 oracle on the first 64 impressions (the per-slot MLP is slow on the CPU)
+    h_off, c_off = syn.csr_offsets(imp.hist_len), syn.csr_offsets(imp.cand_len)
+    out = oracle.final_second_attention_score(sd, table, imp.hist_idx[:h_off[64]], imp.hist_len[sub],
+                                              imp.cand_idx[:c_off[64]], imp.cand_len[sub], dtype=torch.float64)
+    np.testing.assert_allclose(out["scores"], g["scores"][:c_off[64]], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(out["user"].float().numpy()[:32], g["user"], atol=3e-6, rtol=1e-5)
+
+
 def test_latent_user_encoder_long_history_matches_reference(golden_dir):
     """BASELINE configs[4] shape (d=1024, 1024 latents, histories up to 200) through
     get_final_second_attention_score with LatentAttentionModel as the user encoder."""
