@@ -1129,8 +1129,9 @@ def run_reference_gpu(args):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t) / steps
     stage_a = _reference_stage_a_gpu()
+    cfg2 = _reference_cfg2_gpu()
     print(json.dumps({"impl": "reference-gpu", "value": round(n / dt, 1), "unit": UNIT, "ms_per_step": round(dt * 1e3, 1),
-                      "stage_a": stage_a,
+                      "stage_a": stage_a, "cfg2": cfg2,
                       "sample": "%d cfg-4-shaped impressions per step, fp32, %s with DEVICE=cuda (torch %s on %s), user-"
                                 "encoder batch 512" % (n, what, torch.__version__, torch.cuda.get_device_name(0)),
                       "steps": steps}), flush=True)
@@ -1168,6 +1169,41 @@ def _reference_stage_a_gpu():
             out[name + "_news_per_s"] = round(B * reps / (time.perf_counter() - t), 1)
         out["sample"] = "%d x %d items x %d tokens, d=%d, L=%d, reference module on cuda" % (reps, B, S, d, L)
         return out
+    except Exception as exc:  # pragma: no cover - reported, not hidden
+        return {"unavailable": repr(exc)[:300]}
+
+
+def _reference_cfg2_gpu():
+    """BASELINE configs[1] on the reference's torch path: 1,024 impressions (H<=50, C in [3,7]), d=768, N=65,536,
+    FinalAttention user encoder, DEVICE=cuda, one call of get_final_second_attention_score."""
+    try:
+        import pandas as pd
+
+        from oracle import ref_harness
+
+        ref = ref_harness.load_reference(batch_size=512, device="cuda")
+        d, n_rows, n_imp = 768, 65_536, 1024
+        model = ref_harness.make_reference_final_attention(ref, d, HIDDEN, seed=1234)
+        model.load_state_dict(syn.make_final_attention_state_dict(d, HIDDEN, seed=1234))
+        model = model.to("cuda").eval()
+        table = syn.make_table(n_rows, d, seed=1234)
+        imp = syn.make_impressions(n_imp, n_rows, h_max=H_MAX, cand="small", seed=77)
+        hb = pd.Series(np.ones(n_imp, dtype=bool))
+
+        def run():
+            with torch.no_grad():
+                return ref.data_model_helper.get_final_second_attention_score(
+                    imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table, hb, model)
+
+        _quiet(run)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(3):
+            _quiet(run)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) / 3
+        return {"ms_per_call": round(dt * 1e3, 1), "impressions_per_s": round(n_imp / dt, 1),
+                "sample": "1,024 impressions, d=768, N=65,536, fp32, reference torch path with DEVICE=cuda"}
     except Exception as exc:  # pragma: no cover - reported, not hidden
         return {"unavailable": repr(exc)[:300]}
 
