@@ -53,7 +53,34 @@ def test_argument_validation_without_gpu():
     rc = lib.nrb_score_rank(7, 1, 256, 10, 1, 1, 256, 1, 256, None, 1.0, 1, 1, 1, 1, 4, None, 1, None, 1, None)
     assert rc == -1 and b"pool_mode" in lib.nrb_last_error()
     assert lib.nrb_dense_rank(None, None, 0, None, None) == 0  # empty problem is a no-op
+    assert lib.nrb_dense_rank_f64(None, None, 0, None, None) == 0
     assert lib.nrb_final_attention_rows_workspace_bytes(1, 161013, 1024, 4096) > 2 * 16384 * 4096 * 2
+    # round-2 entry points
+    assert lib.nrb_final_attention_rows_split_workspace_bytes(161013, 1024, 4096) >= 16384 * 4096 * (4 + 6)
+    assert lib.nrb_split_rows(1, 1024, 1, 3072, 8, 1022, 0, None) == -1 and b"multiple of 4" in lib.nrb_last_error()
+    assert lib.nrb_split_rows(1, 1024, 1, 3072, 8, 1024, 5, None) == -1 and b"role" in lib.nrb_last_error()
+    assert lib.nrb_convert_rows(1, 7, 8, 1, 1, 8, 4, 8, None) == -1 and b"dtype" in lib.nrb_last_error()
+    assert lib.nrb_narrow_ranks(None, None, 0, None, None) == 0
+    assert lib.nrb_narrow_ranks(4, 8, 16, 12, None) == -1 and b"aligned" in lib.nrb_last_error()
+    assert lib.nrb_mask_to_csr(None, -1, 4, None, None, None, None) == -1
+    assert lib.nrb_push_attach(None, 4, 1) == -1 and b"at most" in lib.nrb_last_error()
+    assert lib.nrb_push_attach(None, 0, 0) == -1 and b"spread" in lib.nrb_last_error()
+    lib.nrb_push_cancel()
+    assert lib.nrb_push_flush(None) == 0  # nothing pending: no launch, no CUDA call
+
+
+def test_host_copy_is_exact_for_any_thread_count():
+    """nrb_host_copy (page cache -> pinned staging of the packed token file) is a plain byte copy."""
+    from news_recommendation_project_v2_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 4095, 3 * (1 << 20) + 17, 9 * (1 << 20)):
+        src = rng.integers(0, 256, size=n, dtype=np.uint8)
+        for nt in (1, 3, 8):
+            dst = np.full(n + 8, 0xAB, dtype=np.uint8)
+            assert lib.nrb_host_copy(dst.ctypes.data if n else None, src.ctypes.data if n else None, n, nt) == 0
+            assert np.array_equal(dst[:n], src) and (dst[n:] == 0xAB).all()
+    assert lib.nrb_host_copy(None, None, 8, 2) == -1
 
 
 def test_state_dict_keys_match_reference(golden_dir):
