@@ -41,9 +41,10 @@ TORCH_DTYPE = torch.float32  # config.py:39
 PRECISION = os.environ.get("NRB200_PRECISION", "bf16")
 
 # Tokens processed per latent-attention chunk (bounds the workspace: ~23 KB / token in bf16 at d=768, L=512, i.e.
-# 6 GB at the default; smaller calls allocate only what they need).  Larger chunks amortise the ~130 us fixed cost
-# of the ten kernels of a chunk: 926 TFLOP/s at 49 k tokens, 980 at 98 k, 997 at 262 k (same box).
-LATENT_MAX_TOKENS = int(os.environ.get("NRB200_LATENT_MAX_TOKENS", "262144"))
+# 12 GB at the default; smaller calls allocate only what they need).  Larger chunks amortise the ~130 us fixed cost
+# of the ten kernels of a chunk: 926 TFLOP/s at 49 k tokens, 980 at 98 k, 997 at 262 k (round 1, same box); round 2,
+# same box: 1,064-1,067 at 262 k, 1,080-1,083 at 524 k, no further gain at 1.3 M.
+LATENT_MAX_TOKENS = int(os.environ.get("NRB200_LATENT_MAX_TOKENS", "524288"))
 
 
 def precision_dtype(precision: str | torch.dtype | None = None) -> torch.dtype:

@@ -235,7 +235,7 @@ def apply_token_attn_packed(model, tok_file, chunk_tokens: Optional[int] = None,
     d = tf.dim
     if d != fw.dim:
         raise _lib.NrbError(f"token dim {d} != model dim {fw.dim}")
-    chunk_tokens = int(chunk_tokens or config.LATENT_MAX_TOKENS)
+    chunk_tokens = int(chunk_tokens or min(config.LATENT_MAX_TOKENS, 262144))  # finer chunks: a fuller pipeline
     longest = int(np.max(np.diff(tf.offsets))) if tf.n_items else 0
     chunk_tokens = max(chunk_tokens, longest, 1)
     bounds = tf.chunk_bounds(chunk_tokens)
