@@ -4,7 +4,6 @@
 //   softmax_groups   : softmax over the latents of one head           -- latent_attention.py:69-72
 //   nrb_final_attention_rows : modeling_utils.py:218-224 hoisted from per-history-slot to per-table-row
 #include "dense.cuh"
-#include "rowops.cuh"
 
 #include <algorithm>
 
@@ -59,18 +58,64 @@ __global__ void __launch_bounds__(256)
 layer_norm_vec_kernel(const void* x, int64_t ldx, const int32_t* row_map, const float* gamma, const float* beta,
                       void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy, int64_t rows,
                       const int* rows_dev, int dim, float eps) {
+  constexpr int EPV = Vec16<TIN>::EPV;
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = rows_dev != nullptr ? min(rows, (int64_t)*rows_dev) : rows;
   const TIN* xin = reinterpret_cast<const TIN*>(x);
-  const size_t yes = y_dtype == NRB_F32 ? 4 : 2;
   for (int64_t r = warp_id; r < n; r += n_warps) {
     const int64_t src = row_map != nullptr ? (int64_t)row_map[r] : r;
-    LnRow<TIN, NV> row;  // rowops.cuh: the same arithmetic the GEMM rider warps run
-    row.load(reinterpret_cast<const char*>(xin + src * ldx), lane, NV);
-    row.finish(lane, NV, dim, eps, gamma, beta, reinterpret_cast<char*>(y) + (size_t)(r * ldy) * yes, y_dtype,
-               copy_f32 != nullptr ? copy_f32 + r * ldcopy : nullptr);
+    const char* base = reinterpret_cast<const char*>(xin + src * ldx);
+    float v[NV][EPV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)(lane + 32 * i) * 16);
+      Vec16<TIN>::unpack(u, v[i]);
+#pragma unroll
+      for (int k = 0; k < EPV; ++k) s += v[i][k];
+    }
+    const float mean = warp_sum(s) / (float)dim;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < EPV; ++k) {
+        const float d = v[i][k] - mean;
+        q = fmaf(d, d, q);
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e0 = (lane + 32 * i) * EPV;
+      float o[EPV];
+#pragma unroll
+      for (int k = 0; k < EPV; k += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + e0 + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + e0 + k);
+        o[k] = (v[i][k] - mean) * rstd * g4.x + b4.x;
+        o[k + 1] = (v[i][k + 1] - mean) * rstd * g4.y + b4.y;
+        o[k + 2] = (v[i][k + 2] - mean) * rstd * g4.z + b4.z;
+        o[k + 3] = (v[i][k + 3] - mean) * rstd * g4.w + b4.w;
+      }
+      if (y_dtype == NRB_BF16) {
+        __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y) + r * ldy + e0;
+#pragma unroll
+        for (int k = 0; k < EPV; k += 4)
+          *reinterpret_cast<uint2*>(yo + k) = make_uint2(pack_bf16x2(o[k], o[k + 1]), pack_bf16x2(o[k + 2], o[k + 3]));
+      } else {
+        float* yo = reinterpret_cast<float*>(y) + r * ldy + e0;
+#pragma unroll
+        for (int k = 0; k < EPV; k += 4) *reinterpret_cast<float4*>(yo + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+      }
+      if (copy_f32 != nullptr) {
+        float* co = copy_f32 + r * ldcopy + e0;
+#pragma unroll
+        for (int k = 0; k < EPV; k += 4)
+          *reinterpret_cast<float4*>(co + k) = make_float4(v[i][k], v[i][k + 1], v[i][k + 2], v[i][k + 3]);
+      }
+    }
   }
 }
 

@@ -12,12 +12,10 @@
 //               on UMMA smem descriptors; fp32 accumulators live in TMEM, double buffered (2 x BN columns)
 //               so the epilogue of tile i overlaps the mainloop of tile i+1; tcgen05.commit frees smem
 //               stages and publishes accumulators.
-//   warp 2    : TMEM allocator, then RIDER: the LayerNorm / masked-mean pass of a neighbouring sub-chunk of stage A
-//               (rowops.cuh) runs here while the tensor pipe is busy -- the GEMMs are tensor bound and leave most of
-//               the HBM bandwidth idle, the passes are pure HBM streams.
+//   warp 2    : TMEM allocator.
 //   warp 3    : all-gather carrier -- when a push job is attached (row-sharded table build) it streams finished
 //               rows of the PREVIOUS chunk to every rank's table with NVLink multicast stores (multimem.st),
-//               so the collective overlaps the tensor-core work inside the same kernel; second rider warp otherwise.
+//               so the collective overlaps the tensor-core work inside the same kernel.
 //   warps 4-11: epilogue     -- two warps per TMEM lane quadrant, 128 accumulator columns each:
 //               tcgen05.ld (32 lanes x 32 columns) -> registers -> fused math -> either
 //                 * bf16 outputs: 128B-swizzled staging tile in smem -> TMA store (coalesced, async), or
@@ -30,7 +28,6 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "ptx.cuh"
-#include "rowops.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -74,9 +71,6 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static_assert(kStages >= 2, "pipeline too shallow");
   static_assert(!kSoftmax || OUT_BF16, "softmax epilogue writes bf16 probabilities");
-  // kernels of the stage-A chain whose idle control warps can carry a rider job (rowops.cuh)
-  static constexpr bool kRider = BN == 256 && (kSoftmax || (EPI == NRB_EPI_RESIDUAL && !OUT_BF16) ||
-                                               (EPI == NRB_EPI_GEGLU && OUT_BF16));
 };
 
 struct GemmParams {
@@ -94,7 +88,6 @@ struct GemmParams {
   int group_valid;  // softmax: valid columns per group (L <= Lp)
   int cluster;      // softmax: CTAs per cluster = max(1, Lp / 256)
   PushJob push;     // rows of an earlier result that the spare warp multicasts to every rank while the GEMM runs
-  RiderJob ride;    // LayerNorm / pooling pass of a neighbouring sub-chunk carried by the idle control warps
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -402,22 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== rider (HBM-bound pass of a neighbouring sub-chunk) =====================
-    if constexpr (Cfg::kRider) {
-      if (p.ride.kind != NRB_RIDE_NONE) {
-        const bool both = p.push.n_seg == 0;  // warp 3 rides too unless it carries the all-gather
-        rider_warp(p.ride, both ? 2 * (int64_t)blockIdx.x : (int64_t)blockIdx.x,
-                   both ? 2 * (int64_t)gridDim.x : (int64_t)gridDim.x, lane);
-      }
-    }
   } else if (warp == 3) {
-    // ===================== all-gather carrier (NVLS multicast stores) / second rider =====================
-    if (p.push.n_seg > 0) {
-      push_job_warp(p.push, blockIdx.x, gridDim.x, lane);
-    } else if constexpr (Cfg::kRider) {
-      if (p.ride.kind != NRB_RIDE_NONE) rider_warp(p.ride, 2 * (int64_t)blockIdx.x + 1, 2 * (int64_t)gridDim.x, lane);
-    }
+    // ===================== all-gather carrier (NVLS multicast stores) =====================
+    if (p.push.n_seg > 0) push_job_warp(p.push, blockIdx.x, gridDim.x, lane);
   } else if (warp >= kCtrlWarps && (warp - kCtrlWarps) < 4 * kHalves) {
     // ===================== epilogue =====================
     const int e = warp - kCtrlWarps;
@@ -735,30 +715,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // ---- host side ---------------------------------------------------------------------------
 
-// rider hand-over: latent.cu announces the pass, the next tcgen05 GEMM launch of this host thread carries it
-static thread_local RiderJob g_next_rider = {};
-void set_next_rider(const RiderJob& job) { g_next_rider = job; }
-bool riders_enabled() {  // NRB200_RIDERS=0: every pass is a kernel of its own (read per call: A/B runs flip it)
-  const char* e = getenv("NRB200_RIDERS");
-  return e == nullptr || e[0] != '0';
-}
-
-// the same device code as a kernel of its own: used when the GEMM variant that follows cannot carry the job
-__global__ void __launch_bounds__(256) rider_kernel(const RiderJob job) {
-  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  rider_warp(job, warp_id, n_warps, threadIdx.x & 31);
-}
-static int run_rider_alone(const RiderJob& job, cudaStream_t st) {
-  const int64_t units = job.kind == NRB_RIDE_POOL ? job.items : (job.rows + 1) / 2;
-  if (units <= 0) return NRB_OK;
-  const int grid = (int)std::min<int64_t>((units + 7) / 8, (int64_t)sm_count_cached() * 8);
-  rider_kernel<<<grid, 256, 0, st>>>(job);
-  note_launch();
-  NRB_CUDA_CHECK(cudaGetLastError());
-  return NRB_OK;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -940,16 +896,6 @@ int gemm_bf16_tc(int epi, int out_dtype, const void* a, int64_t lda, const void*
   p.group_valid = group_valid;
   p.cluster = cluster;
   take_push_share(&p.push);  // a share of the pending all-gather segments rides along (nrb_push_attach)
-  p.ride = g_next_rider;
-  g_next_rider.kind = NRB_RIDE_NONE;
-  if (p.ride.kind != NRB_RIDE_NONE) {
-    const bool capable = !small_n && (softmax || (epi == NRB_EPI_RESIDUAL && out_dtype == NRB_F32) ||
-                                      (epi == NRB_EPI_GEGLU && out_dtype == NRB_BF16));
-    if (!capable) {  // its inputs are complete (they come from earlier launches): run it in front of the GEMM
-      if ((rc = run_rider_alone(p.ride, st)) != NRB_OK) return rc;
-      p.ride.kind = NRB_RIDE_NONE;
-    }
-  }
   if (softmax) return launch_gemm<256, NRB_EPI_SOFTMAX, true>(ma, mw, my, p, st);
   if (small_n) {
     return out_dtype == NRB_BF16 ? dispatch_epi<128, true>(epi, ma, mw, my, p, st)

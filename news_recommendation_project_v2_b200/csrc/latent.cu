@@ -9,12 +9,9 @@
 //                        GEMM(FF2)+bias+residual -> masked mean -> L2 normalise.
 // All contractions go through nrb::linear (tcgen05 for bf16 weights, FFMA for fp32 weights).
 #include "dense.cuh"
-#include "rowops.cuh"
 
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
-#include <vector>
 
 namespace nrb {
 
@@ -119,9 +116,18 @@ pool_items_kernel(const float* h, int64_t ldh, const int32_t* item_off, int seq_
       const int v = tid + k * 256;
       acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (v < nvec) {
-        for (int64_t r = r0; r < r1; ++r) pool_add(acc[k], *reinterpret_cast<const float4*>(h + r * ldh + (size_t)v * 4));
-        pool_mean(acc[k], cnt);  // 0/0 -> NaN for an all-masked item, like the reference
-        ss = __fadd_rn(ss, pool_sq4(acc[k]));
+        for (int64_t r = r0; r < r1; ++r) {
+          const float4 t = *reinterpret_cast<const float4*>(h + r * ldh + (size_t)v * 4);
+          acc[k].x += t.x;
+          acc[k].y += t.y;
+          acc[k].z += t.z;
+          acc[k].w += t.w;
+        }
+        acc[k].x /= cnt;  // 0/0 -> NaN for an all-masked item, like the reference
+        acc[k].y /= cnt;
+        acc[k].z /= cnt;
+        acc[k].w /= cnt;
+        ss += acc[k].x * acc[k].x + acc[k].y * acc[k].y + acc[k].z * acc[k].z + acc[k].w * acc[k].w;
       }
     }
     ss = warp_sum(ss);
@@ -129,12 +135,14 @@ pool_items_kernel(const float* h, int64_t ldh, const int32_t* item_off, int seq_
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot = __fadd_rn(tot, red[w]);
-    const float nrm = pool_norm(tot);
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float nrm = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const int v = tid + k * 256;
-      if (v < nvec) *reinterpret_cast<float4*>(out + i * (int64_t)dim + (size_t)v * 4) = pool_unit(acc[k], nrm);
+      if (v < nvec)
+        *reinterpret_cast<float4*>(out + i * (int64_t)dim + (size_t)v * 4) =
+            make_float4(acc[k].x / nrm, acc[k].y / nrm, acc[k].z / nrm, acc[k].w / nrm);
     }
     __syncthreads();
   }
@@ -165,19 +173,10 @@ static FoldWs fold_ws(void* base, int dim, int heads, int dim_head, int L) {
   return f;
 }
 
-// Workspace of the forward pass.  Up to two SUB-CHUNKS are in flight (set 0 / set 1): their GEMMs alternate, and the
-// HBM-bound passes of one (LayerNorm 1 / 2, masked mean) ride in the idle control warps of the other's GEMM kernels.
-struct PackBufs {
-  int32_t *counts, *item_off, *m_dev, *row_map;
-};
-struct SubSet {
-  PackBufs pk[2];  // the packing of the NEXT sub-chunk of a set is built while the current one is still in use
-  void *xn, *p, *hn, *g;
-  float *logits, *h1;
-};
 struct FwdWs {
-  SubSet set[2];
-  float* h2;  // [cap0 + cap1, dim]: set 1's rows follow set 0's
+  int32_t *counts, *item_off, *m_dev, *row_map;
+  void *xn, *p, *hn, *g;
+  float *logits, *h1, *h2;
   size_t bytes;
 };
 // fused softmax epilogue (logits never leave TMEM): bf16, whole 256-column tiles, a softmax row within one cluster
@@ -185,38 +184,24 @@ static bool fused_softmax(const nrb_latent_weights* w) {
   return w->precision == NRB_BF16 && (w->heads * w->latents_padded) % 256 == 0 && w->latents_padded <= 1024;
 }
 
-static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap0, int64_t items0, int64_t cap1,
-                    int64_t items1) {
+static FwdWs fwd_ws(void* base, const nrb_latent_weights* w, int64_t cap_tokens, int64_t cap_items) {
   const size_t es = dtype_size(w->precision);
   const int64_t hl = (int64_t)w->heads * w->latents_padded;
   Workspace ws(base, (size_t)-1);
   FwdWs f;
-  for (int k = 0; k < 2; ++k) {
-    const int64_t cap = k == 0 ? cap0 : cap1, items = k == 0 ? items0 : items1;
-    SubSet& q = f.set[k];
-    for (int b = 0; b < 2; ++b) {
-      q.pk[b].counts = (int32_t*)ws.take((size_t)items * 4);
-      q.pk[b].item_off = (int32_t*)ws.take((size_t)(items + 1) * 4);
-      q.pk[b].m_dev = (int32_t*)ws.take(16);
-      q.pk[b].row_map = (int32_t*)ws.take((size_t)cap * 4);
-    }
-    q.xn = ws.take((size_t)cap * w->dim * es);
-    q.logits = fused_softmax(w) ? nullptr : (float*)ws.take((size_t)cap * hl * 4);
-    q.p = ws.take((size_t)cap * hl * es);
-    q.h1 = (float*)ws.take((size_t)cap * w->dim * 4);
-    q.hn = ws.take((size_t)cap * w->dim * es);
-    q.g = ws.take((size_t)cap * 4 * w->dim * es);
-  }
-  f.h2 = (float*)ws.take((size_t)(cap0 + cap1) * w->dim * 4);
+  f.counts = (int32_t*)ws.take((size_t)cap_items * 4);
+  f.item_off = (int32_t*)ws.take((size_t)(cap_items + 1) * 4);
+  f.m_dev = (int32_t*)ws.take(16);
+  f.row_map = (int32_t*)ws.take((size_t)cap_tokens * 4);
+  f.xn = ws.take((size_t)cap_tokens * w->dim * es);
+  f.logits = fused_softmax(w) ? nullptr : (float*)ws.take((size_t)cap_tokens * hl * 4);
+  f.p = ws.take((size_t)cap_tokens * hl * es);
+  f.h1 = (float*)ws.take((size_t)cap_tokens * w->dim * 4);
+  f.hn = ws.take((size_t)cap_tokens * w->dim * es);
+  f.g = ws.take((size_t)cap_tokens * 4 * w->dim * es);
+  f.h2 = (float*)ws.take((size_t)cap_tokens * w->dim * 4);
   f.bytes = ws.used + 256;
   return f;
-}
-
-// sub-chunks shorter than this are not worth splitting (wave quantisation of the GEMMs, launch gaps)
-static int64_t min_sub_tokens() {  // read per call: tests and A/B runs flip it at run time
-  const char* e = getenv("NRB200_RIDER_MIN_TOKENS");
-  const long long n = e != nullptr ? atoll(e) : 0;
-  return (int64_t)(n > 0 ? n : 65536);
 }
 
 }  // namespace nrb
@@ -298,211 +283,57 @@ extern "C" int nrb_latent_fold(int precision, int dim, int heads, int dim_head, 
   return NRB_OK;
 }
 
-// ---- the chain over sub-chunks -------------------------------------------------------------------------------------
-// One sub-chunk = a block of token rows that goes through
-//     L1: xn = LN1(x)  ->  S: P = softmax_h(xn A^T)  ->  V: h1 = P B^T + x  ->  L2: hn = LN2(h1)
-//     ->  G: g = GEGLU(hn W1^T + b1)  ->  F: h2 = g W2^T + b2 + h1  ->  PL: pooled = normalize(masked mean(h2))
-// (latent_attention.py:154-170).  S / V / G / F are tcgen05 GEMMs (tensor bound), L1 / L2 / PL are HBM streams.
-struct Sub {
-  int64_t items = 0;     // item mode: items of this sub-chunk
-  int64_t rows_cap = 0;  // token rows (capacity; the effective count is *m_dev when tokens are packed on device)
-  const void* xc = nullptr;
-  const int32_t* mask = nullptr;  // item mode with packing: [items, seq]
-  SubSet* set = nullptr;
-  PackBufs* pk = nullptr;
-  const int32_t* row_map = nullptr;
-  const int* m_dev = nullptr;
-  float* h2 = nullptr;
-  float* pooled = nullptr;  // item mode: this sub-chunk's rows of pooled_out
-};
-
-struct RiderGuard {  // nothing stale may ride in a later, unrelated GEMM launch
-  ~RiderGuard() {
-    RiderJob none = {};
-    set_next_rider(none);
-  }
-};
-
-struct Chain {
-  const nrb_latent_weights* w;
-  int x_dtype, seq;
-  bool pack, pool, ride;
-  cudaStream_t st;
-  int sms;
-
-  int do_pack(Sub& s) const {
-    if (!pack) return NRB_OK;
-    const int g1 = (int)std::min<int64_t>((s.items + 7) / 8, (int64_t)sms * 16);
-    count_valid_kernel<<<g1, 256, 0, st>>>(s.mask, s.items, seq, s.pk->counts); note_launch();
-    scan_items_kernel<<<1, 1024, 0, st>>>(s.pk->counts, s.items, s.pk->item_off, s.pk->m_dev); note_launch();
-    fill_row_map_kernel<<<g1, 256, 0, st>>>(s.mask, s.items, seq, s.pk->item_off, s.pk->row_map); note_launch();
-    NRB_CUDA_CHECK(cudaGetLastError());
-    s.row_map = s.pk->row_map;
-    s.m_dev = s.pk->m_dev;
-    return NRB_OK;
-  }
-  RiderJob ln_job(const void* x, int xdt, const int32_t* row_map, const float* g, const float* b, void* y,
-                  const Sub& s) const {
-    RiderJob j = {};
-    j.kind = NRB_RIDE_LN;
-    j.x = x;
-    j.x_dtype = xdt;
-    j.ldx = w->dim;
-    j.row_map = row_map;
-    j.gamma = g;
-    j.beta = b;
-    j.y = y;
-    j.ldy = w->dim;
-    j.rows = s.rows_cap;
-    j.rows_dev = s.m_dev;
-    j.dim = w->dim;
-    j.eps = 1e-5f;
-    return j;
-  }
-  // xn = LN1(x), gathered through the row map when tokens are packed      latent_attention.py:16
-  RiderJob l1(const Sub& s) const { return ln_job(s.xc, x_dtype, s.row_map, w->ln1_w, w->ln1_b, s.set->xn, s); }
-  // hn = LN2(h1)                                                           :16 (second PreNorm)
-  RiderJob l2(const Sub& s) const { return ln_job(s.set->h1, NRB_F32, nullptr, w->ln2_w, w->ln2_b, s.set->hn, s); }
-  // pooled = normalize(masked mean(h2))                                    :165-170
-  RiderJob pl(const Sub& s) const {
-    RiderJob j = {};
-    j.kind = NRB_RIDE_POOL;
-    j.h = s.h2;
-    j.ldh = w->dim;
-    j.item_off = s.pk->item_off;
-    j.items = s.items;
-    j.out = s.pooled;
-    j.dim = w->dim;
-    return j;
-  }
-  int alone(const RiderJob& j) const {
-    if (j.kind == NRB_RIDE_LN)
-      return layer_norm_rows(j.x, j.x_dtype, j.ldx, j.row_map, j.gamma, j.beta, j.y, w->precision, j.ldy, nullptr, 0,
-                             j.rows, j.rows_dev, j.dim, st, j.eps);
-    const int gp = (int)std::min<int64_t>(j.items, (int64_t)sms * 16);
-    if (gp > 0) {
-      pool_items_kernel<4><<<gp, 256, 0, st>>>(j.h, j.ldh, j.item_off, 0, j.items, j.dim, j.out); note_launch();
-      NRB_CUDA_CHECK(cudaGetLastError());
+// LN -> logits GEMM + per-head softmax -> value GEMM + residual -> LN -> GEGLU GEMM -> output GEMM + residual for
+// `rows_cap` packed token rows (effective count *m_dev when given); h2 receives the fp32 block output.
+static int latent_block_rows(const nrb_latent_weights* w, const FwdWs& f, const void* xc, int x_dtype,
+                             const int32_t* row_map, const int* m_dev, int64_t rows_cap, float* h2, cudaStream_t st) {
+  const int d = w->dim, P = w->precision;
+  const int hl = w->heads * w->latents_padded;
+  int rc;
+    // xn = LN1(x), gathered through the row map when tokens are packed      latent_attention.py:16
+    if ((rc = layer_norm_rows(xc, x_dtype, d, row_map, w->ln1_w, w->ln1_b, f.xn, P, d, nullptr, 0, rows_cap, m_dev, d,
+                              st)) != NRB_OK)
+      return rc;
+    // P = softmax_h(xn A^T)  (SDPA scale folded into A)            :65-72
+    if (fused_softmax(w)) {
+      // fused: logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
+      if ((rc = linear(P, NRB_EPI_SOFTMAX, P, f.xn, d, w->a, d, nullptr, nullptr, 0, f.p, hl, rows_cap, m_dev, hl, d,
+                       st, w->latents_padded, w->num_latents)) != NRB_OK)
+        return rc;
+    } else {
+      if ((rc = linear(P, NRB_EPI_NONE, NRB_F32, f.xn, d, w->a, d, nullptr, nullptr, 0, f.logits, hl, rows_cap,
+                       m_dev, hl, d, st)) != NRB_OK)
+        return rc;
+      if ((rc = softmax_groups(f.logits, hl, f.p, P, hl, rows_cap, m_dev, w->heads, w->latents_padded,
+                               w->num_latents, st)) != NRB_OK)
+        return rc;
     }
-    return NRB_OK;
-  }
-  // hand the pass to the GEMM launch that FOLLOWS (`hosted`), or run it as a kernel of its own
-  int pass(const RiderJob& j, bool hosted) const {
-    const bool fits = j.kind == NRB_RIDE_LN ? rider_ln_ok(j.x_dtype, j.dim) : rider_pool_ok(j.dim);
-    if (ride && hosted && fits) {
-      set_next_rider(j);
-      return NRB_OK;
-    }
-    return alone(j);
-  }
-  // P = softmax_h(xn A^T)  (SDPA scale folded into A)                       :65-72
-  int S(const Sub& s) const {
-    const int d = w->dim, P = w->precision, hl = w->heads * w->latents_padded;
-    if (fused_softmax(w))  // logits never leave TMEM; row statistics exchanged across the cluster through DSMEM
-      return linear(P, NRB_EPI_SOFTMAX, P, s.set->xn, d, w->a, d, nullptr, nullptr, 0, s.set->p, hl, s.rows_cap,
-                    s.m_dev, hl, d, st, w->latents_padded, w->num_latents);
-    int rc = linear(P, NRB_EPI_NONE, NRB_F32, s.set->xn, d, w->a, d, nullptr, nullptr, 0, s.set->logits, hl,
-                    s.rows_cap, s.m_dev, hl, d, st);
-    if (rc != NRB_OK) return rc;
-    return softmax_groups(s.set->logits, hl, s.set->p, P, hl, s.rows_cap, s.m_dev, w->heads, w->latents_padded,
-                          w->num_latents, st);
-  }
-  // h1 = P B^T + x   (the residual operand is the RAW input row, read in place through the row map)   :74, :162
-  int V(const Sub& s) const {
-    const int d = w->dim, hl = w->heads * w->latents_padded;
-    return linear(w->precision, NRB_EPI_RESIDUAL, NRB_F32, s.set->p, hl, w->b, hl, nullptr, s.xc, d, s.set->h1, d,
-                  s.rows_cap, s.m_dev, d, hl, st, 0, 0, x_dtype, s.row_map);
-  }
-  // g = GEGLU(hn W1^T + b1)                                                 :33-35, 24-27
-  int G(const Sub& s) const {
-    const int d = w->dim, P = w->precision;
-    return linear(P, NRB_EPI_GEGLU, P, s.set->hn, d, w->w_ff1, d, w->b_ff1, nullptr, 0, s.set->g, 4 * d, s.rows_cap,
-                  s.m_dev, 8 * d, d, st);
-  }
-  // h2 = g W2^T + b2 + h1                                                   :36, :163
-  int F(const Sub& s) const {
-    const int d = w->dim;
-    return linear(w->precision, NRB_EPI_RESIDUAL, NRB_F32, s.set->g, 4 * d, w->w_ff2, 4 * d, w->b_ff2, s.set->h1, d,
-                  s.h2, d, s.rows_cap, s.m_dev, d, 4 * d, st);
-  }
-
-  // Launch order for a pair (A, B) of sub-chunks; the pass named in brackets rides in that GEMM's idle warps:
-  //   S_A [PL of the previous A]   S_B [PL of the previous B]   V_A [L1 of the next A]   V_B [L2_A]
-  //   G_A [L2_B]                   G_B [L1 of the next B]       F_A                      F_B
-  // (first pair: S_A carries L1_B; last pair: F_B carries PL_A; only L1 of the very first and PL of the very last
-  //  sub-chunk are kernels of their own)
-  // Every pass reads only results of EARLIER launches and is consumed by LATER ones, so kernel boundaries are the
-  // only synchronisation.  With one sub-chunk (or riders off) every pass is a kernel of its own, in program order.
-  int run(Sub* subs, int n) const {
-#define NRB_TRY(expr)                 \
-  do {                                \
-    const int _rc = (expr);           \
-    if (_rc != NRB_OK) return _rc;    \
-  } while (0)
-    RiderGuard guard;
-    for (int i = 0; i < n; i += ride ? 2 : 1) {
-      // without riders the sub-chunks share ONE workspace set and run strictly one after the other
-      Sub& A = subs[i];
-      Sub* B = ride && i + 1 < n ? &subs[i + 1] : nullptr;
-      Sub* nA = ride && i + 2 < n ? &subs[i + 2] : nullptr;
-      Sub* nB = ride && i + 3 < n ? &subs[i + 3] : nullptr;
-      Sub* pA = ride && i >= 2 ? &subs[i - 2] : nullptr;
-      Sub* pB = ride && i >= 2 ? &subs[i - 1] : nullptr;
-      if (i == 0 || !ride) {  // first pair: nothing earlier to ride in
-        NRB_TRY(do_pack(A));
-        NRB_TRY(alone(l1(A)));
-        if (B) NRB_TRY(do_pack(*B));
-      }
-      if (pool && pA)
-        NRB_TRY(pass(pl(*pA), true));
-      else if (i == 0 && B)
-        NRB_TRY(pass(l1(*B), true));
-      NRB_TRY(S(A));
-      if (pool && pB) NRB_TRY(pass(pl(*pB), B != nullptr));
-      if (B) NRB_TRY(S(*B));
-      if (nA) {
-        NRB_TRY(do_pack(*nA));
-        NRB_TRY(pass(l1(*nA), true));
-      }
-      NRB_TRY(V(A));
-      NRB_TRY(pass(l2(A), B != nullptr));
-      if (B) {
-        NRB_TRY(V(*B));
-        NRB_TRY(pass(l2(*B), true));
-      }
-      NRB_TRY(G(A));
-      if (B) {
-        if (nB) {
-          NRB_TRY(do_pack(*nB));
-          NRB_TRY(pass(l1(*nB), true));
-        }
-        NRB_TRY(G(*B));
-      }
-      NRB_TRY(F(A));
-      const bool last = pool && !nA;
-      if (B) {
-        if (last) NRB_TRY(pass(pl(A), true));
-        NRB_TRY(F(*B));
-      }
-      if (last) NRB_TRY(alone(pl(B ? *B : A)));  // nothing left to ride in
-    }
-#undef NRB_TRY
-    return NRB_OK;
-  }
-};
-
-static bool chain_rides(const nrb_latent_weights* w) {
-  return riders_enabled() && w->precision == NRB_BF16 && fused_softmax(w);
+    // h1 = P B^T + x                                               :74, :162
+    // (the residual operand is the RAW input row, read in place through the same row map: no fp32 copy)
+    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.p, hl, w->b, hl, nullptr, xc, d, f.h1, d, rows_cap, m_dev, d, hl,
+                     st, 0, 0, x_dtype, row_map)) != NRB_OK)
+      return rc;
+    // hn = LN2(h1)                                                 :16 (second PreNorm)
+    if ((rc = layer_norm_rows(f.h1, NRB_F32, d, nullptr, w->ln2_w, w->ln2_b, f.hn, P, d, nullptr, 0, rows_cap, m_dev,
+                              d, st)) != NRB_OK)
+      return rc;
+    // g = GEGLU(hn W1^T + b1)                                      :33-35, 24-27
+    if ((rc = linear(P, NRB_EPI_GEGLU, P, f.hn, d, w->w_ff1, d, w->b_ff1, nullptr, 0, f.g, 4 * d, rows_cap, m_dev,
+                     8 * d, d, st)) != NRB_OK)
+      return rc;
+    // h2 = g W2^T + b2 + h1                                        :36, :163
+    if ((rc = linear(P, NRB_EPI_RESIDUAL, NRB_F32, f.g, 4 * d, w->w_ff2, 4 * d, w->b_ff2, f.h1, d, h2, d, rows_cap,
+                     m_dev, d, 4 * d, st)) != NRB_OK)
+      return rc;
+  return NRB_OK;
 }
 
 static int64_t chunk_items_for(int64_t max_tokens, int seq) { return std::max<int64_t>(1, max_tokens / seq); }
 
 extern "C" size_t nrb_latent_forward_workspace_bytes(const nrb_latent_weights* w, int64_t max_tokens) {
   if (w == nullptr || max_tokens <= 0) return 0;
-  // capacity in items is unknown here (depends on seq): bound it by the token capacity (seq >= 1); one sub-chunk of
-  // max_tokens or two of half of it
-  const int64_t half = (max_tokens + 1) / 2;
-  return std::max(fwd_ws(nullptr, w, max_tokens, max_tokens, 0, 0).bytes, fwd_ws(nullptr, w, half, half, half, half).bytes);
+  // capacity in items is unknown here (depends on seq): bound it by max_tokens (seq >= 1)
+  return fwd_ws(nullptr, w, max_tokens, max_tokens).bytes;
 }
 
 extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, int x_dtype, int64_t batch, int seq,
@@ -526,49 +357,44 @@ extern "C" int nrb_latent_forward(const nrb_latent_weights* w, const void* x, in
   if (n_tokens_host) *n_tokens_host = -1;
   if (batch == 0) return NRB_OK;
   NRB_REQUIRE(x && workspace, "nrb_latent_forward: null pointer");
-  // sub-chunks: one of up to max_tokens token slots, or -- when the call is large enough for the HBM-bound passes to
-  // ride in a neighbour's GEMMs -- an even number of up to max_tokens / 2 slots each, two in flight
-  const bool rides = chain_rides(w);
-  const int64_t ib_full = std::min<int64_t>(batch, chunk_items_for(max_tokens, seq));
-  const int64_t ib_half = chunk_items_for(max_tokens / 2, seq);
-  const bool dual = rides && max_tokens / 2 >= seq && batch >= 2 && batch * (int64_t)seq >= 2 * min_sub_tokens() &&
-                    ib_half * seq >= std::min<int64_t>(min_sub_tokens(), batch * (int64_t)seq / 2);
-  int64_t ib = ib_full;
-  if (dual) {
-    int64_t n_sub = (batch + ib_half - 1) / ib_half;
-    n_sub += n_sub & 1;  // pairs
-    ib = (batch + n_sub - 1) / n_sub;
-  }
+  const int64_t ib = std::min<int64_t>(batch, chunk_items_for(max_tokens, seq));
   const int64_t cap = ib * seq;
-  FwdWs f = dual ? fwd_ws(workspace, w, cap, ib, cap, ib) : fwd_ws(workspace, w, cap, ib, 0, 0);
+  FwdWs f = fwd_ws(workspace, w, cap, ib);
   if (workspace_bytes < f.bytes) {
     set_error("nrb_latent_forward: workspace too small (%zu < %zu)", workspace_bytes, f.bytes);
     return NRB_E_WORKSPACE;
   }
+  cudaStream_t st = as_stream(stream);
   const int d = w->dim;
   const size_t xs = dtype_size(x_dtype);
   const bool packed = pooled_out != nullptr;
-  const int64_t n_sub = (batch + ib - 1) / ib;
-  NRB_REQUIRE(n_sub <= (1 << 20), "nrb_latent_forward: too many sub-chunks (raise max_tokens)");
-  std::vector<Sub> subs((size_t)n_sub);
-  for (int64_t k = 0; k < n_sub; ++k) {
-    Sub& s = subs[(size_t)k];
-    const int64_t i0 = k * ib;
-    s.items = std::min<int64_t>(ib, batch - i0);
-    s.rows_cap = s.items * seq;
-    s.xc = (const char*)x + (size_t)i0 * seq * d * xs;
-    s.set = &f.set[dual ? (k & 1) : 0];
+  const int sms = sm_count_cached();
+  for (int64_t i0 = 0; i0 < batch; i0 += ib) {
+    const int64_t items = std::min<int64_t>(ib, batch - i0);
+    const int64_t rows_cap = items * seq;
+    const void* xc = (const char*)x + (size_t)i0 * seq * d * xs;
+    const int32_t* row_map = nullptr;
+    const int* m_dev = nullptr;
+    int rc;
     if (packed) {
-      s.mask = token_mask + i0 * seq;
-      s.pk = &s.set->pk[dual ? ((k >> 1) & 1) : 0];
-      s.h2 = f.h2 + (dual && (k & 1) ? (size_t)cap * d : 0);
-      s.pooled = pooled_out + i0 * d;
-    } else {
-      s.h2 = unpooled_out + (size_t)i0 * seq * d;
+      const int32_t* mk = token_mask + i0 * seq;
+      const int g1 = (int)std::min<int64_t>((items + 7) / 8, (int64_t)sms * 16);
+      count_valid_kernel<<<g1, 256, 0, st>>>(mk, items, seq, f.counts); note_launch();
+      scan_items_kernel<<<1, 1024, 0, st>>>(f.counts, items, f.item_off, f.m_dev); note_launch();
+      fill_row_map_kernel<<<g1, 256, 0, st>>>(mk, items, seq, f.item_off, f.row_map); note_launch();
+      NRB_CUDA_CHECK(cudaGetLastError());
+      row_map = f.row_map;
+      m_dev = f.m_dev;
+    }
+    float* h2 = packed ? f.h2 : unpooled_out + (size_t)i0 * seq * d;
+    if ((rc = latent_block_rows(w, f, xc, x_dtype, row_map, m_dev, rows_cap, h2, st)) != NRB_OK) return rc;
+    if (packed) {
+      const int gp = (int)std::min<int64_t>(items, (int64_t)sms * 16);
+      pool_items_kernel<4><<<gp, 256, 0, st>>>(f.h2, d, f.item_off, seq, items, d, pooled_out + i0 * d); note_launch();
+      NRB_CUDA_CHECK(cudaGetLastError());
     }
   }
-  Chain c{w, x_dtype, seq, packed, packed, rides && dual, as_stream(stream), sm_count_cached()};
-  return c.run(subs.data(), (int)n_sub);
+  return NRB_OK;
 }
 
 // Varlen entry: tokens already packed [n_tokens, dim] with CSR item offsets (device int32 [batch+1]); this is the
@@ -593,29 +419,14 @@ extern "C" int nrb_latent_forward_packed(const nrb_latent_weights* w, const void
     return NRB_OK;
   }
   NRB_REQUIRE(x_packed && item_off && pooled_out && workspace, "nrb_latent_forward_packed: null pointer");
-  // rows are independent until the pooling: two sub-chunks of rows (split anywhere, not at item boundaries) let the
-  // LayerNorm passes ride; the pooling runs over all rows afterwards
-  const bool dual = chain_rides(w) && n_tokens >= 2 * min_sub_tokens();
-  const int64_t cap0 = dual ? ((n_tokens / 2 + 127) / 128) * 128 : n_tokens;
-  const int64_t cap1 = n_tokens - cap0;
-  FwdWs f = fwd_ws(workspace, w, cap0, 0, cap1, 0);
+  FwdWs f = fwd_ws(workspace, w, n_tokens, 1);
   if (workspace_bytes < f.bytes) {
     set_error("nrb_latent_forward_packed: workspace too small (%zu < %zu)", workspace_bytes, f.bytes);
     return NRB_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
   int rc;
-  Sub subs[2];
-  subs[0].rows_cap = cap0;
-  subs[0].xc = x_packed;
-  subs[0].set = &f.set[0];
-  subs[0].h2 = f.h2;
-  subs[1].rows_cap = cap1;
-  subs[1].xc = (const char*)x_packed + (size_t)cap0 * w->dim * dtype_size(x_dtype);
-  subs[1].set = &f.set[1];
-  subs[1].h2 = f.h2 + (size_t)cap0 * w->dim;
-  Chain c{w, x_dtype, 0, false, false, dual, st, sm_count_cached()};
-  if ((rc = c.run(subs, dual ? 2 : 1)) != NRB_OK) return rc;
+  if ((rc = latent_block_rows(w, f, x_packed, x_dtype, nullptr, nullptr, n_tokens, f.h2, st)) != NRB_OK) return rc;
   const int gp = (int)std::min<int64_t>(batch, (int64_t)sm_count_cached() * 16);
   pool_items_kernel<4><<<gp, 256, 0, st>>>(f.h2, w->dim, item_off, 0, batch, w->dim, pooled_out); note_launch();
   NRB_CUDA_CHECK(cudaGetLastError());

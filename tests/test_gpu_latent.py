@@ -204,51 +204,3 @@ def test_packed_all_empty_items_give_nan():
     assert torch.isnan(out[[0, 2, 4]]).all() and torch.isfinite(out[[1, 3]]).all()
     want = m.forward_packed(tok.cuda(), torch.tensor([0, 4, 10])).cpu()
     assert torch.equal(out[[1, 3]], want)
-
-
-@pytest.mark.parametrize("dim,L,heads,dh", [(256, 40, 4, 64), (768, 512, 8, 64), (1024, 1024, 8, 64)])
-def test_riding_passes_are_bit_invisible(monkeypatch, dim, L, heads, dh):
-    """Two sub-chunks in flight with LayerNorm 1 / 2 and the masked mean RIDING in the idle control warps of the
-    neighbour's tcgen05 GEMMs == every pass as a kernel of its own, bit for bit: padded + masked forward (fp32 and bf16
-    tokens, all-masked item), un-pooled forward and the packed entry; 1, 4, 11 pairs and an odd sub-chunk count."""
-    from news_recommendation_project_v2_b200 import _lib, config
-    launches = _lib.load().nrb_kernel_launches
-    m = _model(dim, L, 11, "bf16", heads=heads, dim_head=dh)
-    B, S = 150, 24
-    x, mask = syn.make_token_batch(B, S, dim, seed=12, min_len=1)
-    mask[9] = 0
-    mask[11, :] = torch.tensor([0, 1] * 12)
-    keep = [i for i in range(B) if i != 9]
-    xs = {"fp32": x.cuda(), "bf16": x.to(torch.bfloat16).cuda()}
-    mk = mask.cuda()
-    lens = mask.sum(1)
-    off = torch.zeros(B + 1, dtype=torch.int64)
-    off[1:] = torch.cumsum(lens, 0)
-    packed = x[mask.bool()].to(torch.bfloat16).cuda()
-    old = config.LATENT_MAX_TOKENS
-    try:
-        config.LATENT_MAX_TOKENS = 1 << 20
-        monkeypatch.setenv("NRB200_RIDERS", "0")
-        want = {k: m(v, mk).cpu() for k, v in xs.items()}
-        want_un = m(xs["bf16"], None).cpu()
-        want_pk = m.forward_packed(packed, off).cpu()
-        n0 = launches()
-        m(xs["bf16"], mk)
-        alone_launches = launches() - n0
-        monkeypatch.setenv("NRB200_RIDERS", "1")
-        monkeypatch.setenv("NRB200_RIDER_MIN_TOKENS", "64")
-        for mt in (1 << 20, S * 40, S * 14, S * 12):
-            config.LATENT_MAX_TOKENS = mt
-            for k, v in xs.items():
-                got = m(v, mk).cpu()
-                assert torch.isnan(got[9]).all() and torch.equal(got[keep], want[k][keep]), (k, mt)
-            assert torch.equal(m(xs["bf16"], None).cpu(), want_un), mt
-        config.LATENT_MAX_TOKENS = 1 << 20
-        got_pk = m.forward_packed(packed, off).cpu()
-        assert torch.isnan(got_pk[9]).all() and torch.equal(got_pk[keep], want_pk[keep])
-        # one pair: 3 + 3 packing kernels, 8 GEMMs, the first LN1 and the last pooling alone -- the other 4 passes ride
-        n0 = launches()
-        m(xs["bf16"], mk)
-        assert launches() - n0 == 16 and alone_launches == 10
-    finally:
-        config.LATENT_MAX_TOKENS = old
