@@ -54,7 +54,7 @@ layer_norm_kernel(const void* x, int x_dtype, int64_t ldx, const int32_t* row_ma
 // Vectorised single-pass variant: the row lives in registers (NV 16-byte vectors per lane), so x is read
 // once; used whenever dim*elemsize is a multiple of 512 bytes (768 / 1024-wide rows in both dtypes).
 template <typename TIN, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 3 ? 3 : 2)
 layer_norm_vec_kernel(const void* x, int64_t ldx, const int32_t* row_map, const float* gamma, const float* beta,
                       void* y, int y_dtype, int64_t ldy, float* copy_f32, int64_t ldcopy, int64_t rows,
                       const int* rows_dev, int dim, float eps) {
@@ -64,8 +64,11 @@ layer_norm_vec_kernel(const void* x, int64_t ldx, const int32_t* row_map, const 
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = rows_dev != nullptr ? min(rows, (int64_t)*rows_dev) : rows;
   const TIN* xin = reinterpret_cast<const TIN*>(x);
+  // the row-map entry of the NEXT row is requested one row ahead: the gather costs no dependent-load latency
+  int64_t src_next = warp_id < n ? (row_map != nullptr ? (int64_t)row_map[warp_id] : warp_id) : 0;
   for (int64_t r = warp_id; r < n; r += n_warps) {
-    const int64_t src = row_map != nullptr ? (int64_t)row_map[r] : r;
+    const int64_t src = src_next;
+    if (r + n_warps < n) src_next = row_map != nullptr ? (int64_t)row_map[r + n_warps] : r + n_warps;
     const char* base = reinterpret_cast<const char*>(xin + src * ldx);
     float v[NV][EPV];
     float s = 0.f;

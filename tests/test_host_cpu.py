@@ -454,3 +454,22 @@ def test_sass_contains_the_blackwell_instructions():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "LDG.E.128"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS"
+
+
+def test_balanced_cuts_match_full_array_search():
+    """score_host's chunk plan by bisection == np.searchsorted over the full cost array; the tapered plan only adds
+    cuts inside the last chunk."""
+    from news_recommendation_project_v2_b200.engine import _balanced_cuts
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 1000, 50_000):
+        ho = np.concatenate([[0], np.cumsum(rng.integers(0, 51, n))]).astype(np.int64)
+        co = np.concatenate([[0], np.cumsum(rng.integers(1, 55, n))]).astype(np.int64)
+        cost = 2 * ho + co
+        for nc in (1, 3, 8, 16):
+            k = max(1, min(nc, n))
+            want = sorted(set([0] + np.searchsorted(cost, cost[-1] * np.arange(1, k) / k).tolist() + [n]))
+            got = _balanced_cuts(ho, co, n, k)
+            assert got == want
+            tapered = _balanced_cuts(ho, co, n, k, taper=True)
+            assert set(got) <= set(tapered) and tapered == sorted(tapered) and tapered[0] == 0 and tapered[-1] == n
+            assert all(c >= got[-2] for c in set(tapered) - set(got))
