@@ -85,6 +85,12 @@ def _final_attention_weights(model, dtype: torch.dtype, device) -> dict:
     return w
 
 
+def _mark(stream) -> "torch.cuda.Event":
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record(stream)
+    return ev
+
+
 def _balanced_cuts(ho: np.ndarray, co: np.ndarray, n_imp: int, n_chunks: int, taper: bool = False) -> list:
     """Impression boundaries that split cost(i) = 2 * ho[i] + co[i] (table rows read up to impression i) evenly:
     the first i with cost(i) >= k / n_chunks of the total, by bisection on the two offset arrays -- a dozen
@@ -92,8 +98,11 @@ def _balanced_cuts(ho: np.ndarray, co: np.ndarray, n_imp: int, n_chunks: int, ta
     total = 2 * int(ho[n_imp]) + int(co[n_imp])
     cuts = {0, n_imp}
     fracs = [k / n_chunks for k in range(1, n_chunks)]
-    if taper and n_chunks >= 4:  # the results of the LAST chunk cross PCIe after all kernels are done: keep it small
-        fracs += [1 - 1 / (2 * n_chunks), 1 - 1 / (4 * n_chunks)]
+    if taper and n_chunks >= 2:  # the results of the LAST piece cross PCIe after all kernels are done: keep it small
+        last = 1 / n_chunks
+        while last > 1 / 32:
+            last /= 2
+            fracs.append(1 - last)
     for f in fracs:
         target = total * f
         lo, hi = 0, n_imp
@@ -242,19 +251,25 @@ class ScoringEngine:
                     ev = torch.cuda.Event()
                     ev.record(s_in)
                 evs.append((i0, i1, c0, c1, ev))
+            trace = getattr(self, "_trace", None)  # diagnosis only (tools/e2e_timeline.py): [(label, event)]
             for i0, i1, c0, c1, ev in evs:
                 cur.wait_event(ev)
+                if trace is not None:
+                    trace.append(("h2d_ready+wait %d" % i0, _mark(cur)))
                 ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hi_d, ho_d[i0:i1 + 1], ci_d,
                                co_d[i0:i1 + 1], n_c, want_ranks=True, err_flag=flag, out_scores=sc_d, out_ranks=rk_d)
                 if narrow and c1 > c0:
                     a0 = c0 - (c0 % 8)  # 16-byte aligned window (the overlap rewrites identical values)
                     ops.narrow_ranks(rk_d[a0:c1], rk16_d[a0:c1], flag)
-                done = torch.cuda.Event()
+                done = torch.cuda.Event(enable_timing=trace is not None)
                 done.record(cur)
                 s_out.wait_event(done)
                 with torch.cuda.stream(s_out):
                     scores_out[c0:c1].copy_(sc_d[c0:c1], non_blocking=True)
                     ranks_out[c0:c1].copy_((rk16_d if narrow else rk_d)[c0:c1], non_blocking=True)
+                    if trace is not None:
+                        trace.append(("kernel_done %d" % i0, done))
+                        trace.append(("d2h_done %d" % i0, _mark(s_out)))
             s_in.synchronize()
             s_out.synchronize()
             cur.synchronize()
