@@ -209,7 +209,10 @@ class ScoringEngine:
 
         hist_idx / cand_idx int32, hist_off / cand_off int64 [I+1] CPU tensors.  `ranks_out` may be int32 or int16:
         int16 ranks are narrowed on the device and cross PCIe at 2 bytes per candidate (6 instead of 8 bytes of
-        results per candidate; a rank above 32767 raises OverflowError)."""
+        results per candidate; a rank above 32767 raises OverflowError).
+
+        The device staging belongs to the engine: one `score_host` call per engine at a time (the reference issues all
+        GPU work from one thread).  The call returns after its results have landed in the host buffers."""
         dev = self.device
         n_imp = hist_off.numel() - 1
         assert cand_off.numel() - 1 == n_imp, "Number of rows should be consistent"
