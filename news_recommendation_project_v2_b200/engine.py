@@ -254,12 +254,13 @@ class ScoringEngine:
                     ev = torch.cuda.Event()
                     ev.record(s_in)
                 evs.append((i0, i1, c0, c1, ev))
+            k_x, k_e, k_c = self._kernel_tables()
             trace = getattr(self, "_trace", None)  # diagnosis only (tools/e2e_timeline.py): [(label, event)]
             for i0, i1, c0, c1, ev in evs:
                 cur.wait_event(ev)
                 if trace is not None:
                     trace.append(("h2d_ready+wait %d" % i0, _mark(cur)))
-                ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hi_d, ho_d[i0:i1 + 1], ci_d,
+                ops.score_rank(self.pool_mode, k_x, k_e, k_c, hi_d, ho_d[i0:i1 + 1], ci_d,
                                co_d[i0:i1 + 1], n_c, want_ranks=True, err_flag=flag, out_scores=sc_d, out_ranks=rk_d)
                 if narrow and c1 > c0:
                     a0 = c0 - (c0 % 8)  # 16-byte aligned window (the overlap rewrites identical values)
@@ -279,6 +280,24 @@ class ScoringEngine:
             self._staging_busy = False
             ops.raise_on_index_error(flag, "score_host")
         return scores_out, ranks_out
+
+    # -- tables as the fused kernel wants them -----------------------------------------------------------
+    def _kernel_tables(self):
+        """(hist_x, hist_e, cand) for `nrb_score_rank`, whose lanes own whole 16-byte vectors of a 512-byte multiple
+        row.  The reference's usual widths (1024, 768, 512, 256) are that already and pass through untouched; any other
+        width (384: bge-small, config.py:63) gets zero-padded copies of the three tables -- zero columns change no
+        pooled value, dot product or norm, so scores and ranks are those of the logical width."""
+        es = self.cand.element_size()
+        d = self.cand.shape[1]
+        if (d * es) % 512 == 0:
+            return self.hist_x, self.hist_e, self.cand
+        key = tuple((t.data_ptr(), t._version) for t in (self.hist_x, self.hist_e, self.cand) if t is not None)
+        hit = getattr(self, "_padded", None)
+        if hit is None or hit[0] != key:
+            pad = lambda t: None if t is None else ops.pad_rows_for_kernel(t)
+            hit = (key, (pad(self.hist_x), pad(self.hist_e), pad(self.cand)))
+            self._padded = hit
+        return hit[1]
 
     # -- per-row user-encoder transform (dense, once per table) --------------------------------
     def prepare_user_encoder(self, hist_src: torch.Tensor) -> None:
@@ -324,10 +343,14 @@ class ScoringEngine:
                      want_ranks=True, err_flag=None, out_scores=None, out_ranks=None, cand_base=None,
                      blend_alpha: float = 1.0):
         with torch.cuda.device(self.device):
-            return ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand, hist_idx_d, hist_off_d,
-                                  cand_idx_d, cand_off_d, n_cand, want_user=want_user, want_ranks=want_ranks,
-                                  err_flag=err_flag, out_scores=out_scores, out_ranks=out_ranks, cand_base=cand_base,
-                                  blend_alpha=blend_alpha)
+            k_x, k_e, k_c = self._kernel_tables()
+            user, scores, ranks = ops.score_rank(self.pool_mode, k_x, k_e, k_c, hist_idx_d, hist_off_d,
+                                                 cand_idx_d, cand_off_d, n_cand, want_user=want_user,
+                                                 want_ranks=want_ranks, err_flag=err_flag, out_scores=out_scores,
+                                                 out_ranks=out_ranks, cand_base=cand_base, blend_alpha=blend_alpha)
+            if user is not None and user.shape[1] != self.cand.shape[1]:
+                user = user[:, :self.cand.shape[1]].contiguous()  # drop the kernel's zero padding
+            return user, scores, ranks
 
     def score(self, hist_idx, hist_len, cand_idx, cand_len, want_user=False, want_ranks=True, cand_base=None,
               blend_alpha: float = 1.0):
@@ -353,10 +376,11 @@ class ScoringEngine:
             assert n_h == len(hist_idx)
             zeros = torch.zeros(n_imp + 1, dtype=torch.int64, device=self.device)
             empty = torch.zeros(1, dtype=torch.int32, device=self.device)
-            user, _, _ = ops.score_rank(self.pool_mode, self.hist_x, self.hist_e, self.cand,
+            k_x, k_e, k_c = self._kernel_tables()
+            user, _, _ = ops.score_rank(self.pool_mode, k_x, k_e, k_c,
                                         _as_i32(hist_idx, self.device), h_off, empty, zeros, 0, want_user=True,
                                         want_ranks=False)
-            return user
+            return user if user.shape[1] == self.cand.shape[1] else user[:, :self.cand.shape[1]].contiguous()
 
 
 _engine_cache: dict = {}

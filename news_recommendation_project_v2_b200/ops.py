@@ -125,15 +125,42 @@ def pool_masked_rows(x: torch.Tensor, e: torch.Tensor, attention_mask: torch.Ten
     return user
 
 
+def pad_rows_for_kernel(t: torch.Tensor) -> torch.Tensor:
+    """[rows, d] -> [rows, d rounded up to a 512-byte multiple], zero filled (native strided row copy)."""
+    es = t.element_size()
+    quantum = 512 // es
+    rows, d = t.shape
+    dpad = (d + quantum - 1) // quantum * quantum
+    if dpad == d:
+        return t
+    out = torch.zeros(rows, dpad, dtype=t.dtype, device=t.device)
+    if rows:
+        convert_rows(t, t.dtype, out=out[:, :d])
+    return out
+
+
 def score_rank(pool_mode: int, hist_x: torch.Tensor, hist_e: Optional[torch.Tensor], cand: torch.Tensor,
                hist_idx: torch.Tensor, hist_off: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
                n_cand_total: int, want_user: bool = False, want_ranks: bool = True,
                err_flag: Optional[torch.Tensor] = None, out_scores: Optional[torch.Tensor] = None,
                out_ranks: Optional[torch.Tensor] = None, cand_base: Optional[torch.Tensor] = None,
                blend_alpha: float = 1.0):
-    """Fused gather -> user vector -> cosine (-> blend with a per-row baseline) -> dense rank (nrb_score_rank)."""
+    """Fused gather -> user vector -> cosine (-> blend with a per-row baseline) -> dense rank (nrb_score_rank).
+
+    Row widths that are not a multiple of 512 bytes (e.g. 384 bf16 elements) run on zero-padded copies of the tables
+    (`pad_rows_for_kernel`; the engine caches its own): zero columns change no pooled value, dot product or norm."""
     dev = require_device(hist_x.device)
     _dev(hist_x, "hist_x")
+    if hist_x.dim() == 2 and (hist_x.shape[1] * hist_x.element_size()) % 512 != 0:
+        d = hist_x.shape[1]
+        px = pad_rows_for_kernel(hist_x)
+        pc = px if cand is hist_x else pad_rows_for_kernel(_dev(cand, "cand", hist_x.dtype))
+        pe = None if hist_e is None else pad_rows_for_kernel(_dev(hist_e, "hist_e", hist_x.dtype))
+        user, scores, ranks = score_rank(pool_mode, px, pe, pc, hist_idx, hist_off, cand_idx, cand_off, n_cand_total,
+                                         want_user=want_user, want_ranks=want_ranks, err_flag=err_flag,
+                                         out_scores=out_scores, out_ranks=out_ranks, cand_base=cand_base,
+                                         blend_alpha=blend_alpha)
+        return (None if user is None else user[:, :d].contiguous()), scores, ranks
     _dev(cand, "cand", hist_x.dtype)
     if hist_e is not None:
         _dev(hist_e, "hist_e", hist_x.dtype)

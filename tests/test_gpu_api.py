@@ -402,3 +402,52 @@ def test_final_score_blend_and_classification_head(golden_dir, precision, tol):
     want = oracle.final_score(attn_sd, table, hist_idx, hist_len, imp.cand_idx, imp.cand_len, hb, g["classification"],
                               alpha_param=60.0)["scores"]  # sigmoid(60) == 1: pure cosine where there is history
     np.testing.assert_allclose(only["scores"], want, atol=tol, rtol=0)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 5e-3)])
+def test_row_width_384_runs_on_zero_padded_tables(precision, tol):
+    """Embedding widths that are not a multiple of 512 bytes (384: bge-small, reference config.py:63) go through
+    zero-padded copies of the tables: same scores / ranks / user vectors as the oracle at the logical width, on the
+    engine path, the pipelined host path, the module forward and the latent user encoder."""
+    from news_recommendation_project_v2_b200.data_model_helper import get_final_second_attention_score
+    from news_recommendation_project_v2_b200.data_utils import final_attention_eval_collate_fn, group_items
+    from news_recommendation_project_v2_b200.engine import ScoringEngine
+    from news_recommendation_project_v2_b200.latent_attention import LatentAttentionModel
+    dim, hidden, n_rows, n_imp = 384, 512, 3000, 150
+    model = _final_model(dim, hidden, 71, precision)
+    table = syn.make_table(n_rows, dim, seed=72)
+    imp = syn.make_impressions(n_imp, n_rows, h_max=50, cand="large", seed=73)
+    ref = oracle.final_second_attention_score(model.state_dict(), table, imp.hist_idx, imp.hist_len, imp.cand_idx,
+                                              imp.cand_len)
+    out = get_final_second_attention_score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table,
+                                           np.ones(n_imp, dtype=bool), model, precision=precision)
+    np.testing.assert_allclose(out["scores"], ref["scores"], atol=tol, rtol=0)
+    ranks = np.concatenate([np.asarray(r) for r in out["grouped_scores"]])
+    assert np.array_equal(ranks, np.concatenate(oracle.rank_group_preds(out["scores"], imp.cand_len)))
+    hard, _ = _rank_mismatches(ranks, np.concatenate(ref["grouped_scores"]), ref["scores"], imp.cand_len, 2 * tol)
+    assert hard == 0
+    # user vectors at the logical width; host pipeline == device path bit for bit
+    eng = ScoringEngine(table, model, precision=precision)
+    user, s_dev, r_dev = eng.score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, want_user=True)
+    assert user.shape == (n_imp, dim) and eng.cand.shape == (n_rows, dim)
+    want_u = oracle.user_vectors(model.state_dict(), table, imp.hist_idx, imp.hist_len)
+    np.testing.assert_allclose(user.cpu().numpy(), want_u.float().numpy(), atol=2e-5 if precision == "fp32" else 2e-2, rtol=0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    s_h, r_h = eng.score_host(t(imp.hist_idx), t(syn.csr_offsets(imp.hist_len)), t(imp.cand_idx),
+                              t(syn.csr_offsets(imp.cand_len)), n_chunks=3)
+    assert torch.equal(s_h, s_dev.cpu()) and torch.equal(r_h, r_dev.cpu())
+    # module forward on a padded, masked batch
+    groups = group_items(imp.hist_idx[:int(imp.hist_len[:20].sum())], imp.hist_len[:20])
+    emb, mask = final_attention_eval_collate_fn(list(groups), table)
+    got = model(emb.cuda(), mask.cuda())
+    want = oracle.final_attention(model.state_dict(), emb, mask)
+    torch.testing.assert_close(got.cpu().double(), want, atol=2e-5 if precision == "fp32" else 2e-2, rtol=2e-2)
+    # latent model as user encoder at the same width
+    m = LatentAttentionModel(dim=dim, num_latents=32, heads=2, dim_head=64, precision=precision).eval()
+    m.load_state_dict(syn.make_latent_state_dict(dim, 32, heads=2, dim_head=64, seed=74))
+    out = get_final_second_attention_score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len, table,
+                                           np.ones(n_imp, dtype=bool), m, precision=precision)
+    emb, msk = oracle.final_attention_eval_collate(oracle.group_items(imp.hist_idx, imp.hist_len), table)
+    u = oracle.latent_pool(m.state_dict(), emb, msk, heads=2, dim_head=64)
+    want = oracle.cosine_scores(u, table, imp.cand_idx, imp.cand_len).numpy()
+    np.testing.assert_allclose(out["scores"], want, atol=tol, rtol=0)
