@@ -169,34 +169,54 @@ class PackedTokenFile:
             raise ValueError(f"{path} is not a packed token file")
         self.path, self.dim, self.n_items, self.n_tokens = path, int(dim), int(n_items), int(n_tok)
         self.dtype, npdt, self.elem_size = _DTYPES[code]
+        self._tok_off = int(tok_off)
         self.offsets = np.memmap(path, dtype=np.int64, mode="r", offset=off_off, shape=(self.n_items + 1,))
         self.tokens_raw = np.memmap(path, dtype=npdt, mode="r", offset=tok_off, shape=(self.n_tokens, self.dim)) \
             if self.n_tokens else np.zeros((0, self.dim), dtype=npdt)
 
     def register(self) -> bool:
-        """Page-lock the mapped token section for the GPU (cudaHostRegister, read-only): chunks then cross PCIe by DMA
-        straight from the page cache, with no staging copy.  Returns False when the driver refuses (then
-        `apply_token_attn_packed` stages through pinned buffers)."""
+        """Page-lock the mapped token section for the GPU (cudaHostRegister): chunks then cross PCIe by DMA straight
+        from the page cache, with no staging copy.  Tried first on the read-only mapping (cudaHostRegisterReadOnly),
+        then -- where the driver refuses read-only registrations and the file is writable -- on a shared read-write
+        mapping of the same pages (nothing is ever written through it).  Returns False when both are refused (then
+        `apply_token_attn_packed` stages through pinned buffers); `register_error` keeps the CUDA error codes."""
         if getattr(self, "_registered", False):
             return True
         if not self.n_tokens or not torch.cuda.is_available():
             return False
-        try:
-            rt = torch.cuda.cudart()
-            addr, nbytes = self.tokens_raw.ctypes.data, self.tokens_raw.nbytes
-            err = rt.cudaHostRegister(addr, nbytes, 8)  # cudaHostRegisterReadOnly
-            ok = int(err) == 0 if not isinstance(err, tuple) else int(err[0]) == 0
-            if ok:
-                probe = torch.from_numpy(self.tokens_raw[:1])
-                ok = bool(probe.is_pinned())
-                if not ok:
-                    rt.cudaHostUnregister(addr)
-            self._registered = ok
-        except Exception:
-            self._registered = False
-        if not self._registered:
+        self.register_error = []
+        attempts = [(self.tokens_raw, 8)]  # cudaHostRegisterReadOnly on the existing mapping
+        if os.access(self.path, os.W_OK):
+            attempts.append((None, 0))  # shared read-write mapping, default flags
+        for mapping, flags in attempts:
+            try:
+                if mapping is None:
+                    mapping = np.memmap(self.path, dtype=self.tokens_raw.dtype, mode="r+", offset=self._tok_off,
+                                        shape=(self.n_tokens, self.dim))
+                rt = torch.cuda.cudart()
+                addr, nbytes = mapping.ctypes.data, mapping.nbytes
+                err = rt.cudaHostRegister(addr, nbytes, flags)
+                code = int(err[0]) if isinstance(err, tuple) else int(err)
+                ok = code == 0
+                if ok:
+                    import warnings
+
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")  # read-only mapping: torch never writes through this view
+                        ok = bool(torch.from_numpy(mapping[:1]).is_pinned())
+                    if not ok:
+                        rt.cudaHostUnregister(addr)
+                        code = -1
+                self.register_error.append((flags, code))
+                if ok:
+                    self.tokens_raw = mapping
+                    self._registered = True
+                    return True
+            except Exception as exc:  # noqa: BLE001 -- any refusal means "stage through pinned buffers"
+                self.register_error.append((flags, repr(exc)[:120]))
             _clear_cuda_last_error()  # a refused registration must not surface later as somebody else's error
-        return self._registered
+        self._registered = False
+        return False
 
     def unregister(self) -> None:
         if getattr(self, "_registered", False):

@@ -165,7 +165,18 @@ def test_packed_token_file_pipeline_equals_padded_forward(tmp_path):
     g = torch.Generator().manual_seed(5)
     items = [torch.randn(int(n), 256, generator=g).to(torch.bfloat16) for n in torch.randint(1, 40, (83,), generator=g)]
     items[17] = items[17][:0]  # an empty item
-    path = str(tmp_path / "tok.nrbtok")
+    # /dev/shm when there is one: shared-memory pages are what cudaHostRegister accepts (the zero-copy branch below)
+    shm = os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK)
+    path = "/dev/shm/nrb200_test_%d.nrbtok" % os.getpid() if shm else str(tmp_path / "tok.nrbtok")
+    try:
+        _packed_file_checks(m, items, path)
+    finally:
+        if shm and os.path.exists(path):
+            os.remove(path)
+
+
+def _packed_file_checks(m, items, path):
+    from news_recommendation_project_v2_b200.token_store import apply_token_attn_packed, write_packed_tokens
     write_packed_tokens(path, items, 256)
     S = max(t.shape[0] for t in items)
     x = torch.zeros(len(items), S, 256, dtype=torch.bfloat16)
@@ -183,9 +194,12 @@ def test_packed_token_file_pipeline_equals_padded_forward(tmp_path):
     from news_recommendation_project_v2_b200.token_store import PackedTokenFile
     tf = PackedTokenFile(path)
     if tf.register():
-        got = apply_token_attn_packed(m, tf, chunk_tokens=333)
-        assert torch.equal(got[keep], want[keep])
+        for chunk in (40, 333, 1 << 20):
+            got = apply_token_attn_packed(m, tf, chunk_tokens=chunk)
+            assert torch.isnan(got[17]).all() and torch.equal(got[keep], want[keep])
         tf.unregister()
+    else:
+        print("cudaHostRegister refused the mapping:", tf.register_error)
 
 
 def test_packed_all_empty_items_give_nan():
