@@ -481,6 +481,16 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     return y
 
 
+_aux_streams: dict = {}
+
+
+def _aux_stream(dev: torch.device) -> "torch.cuda.Stream":
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _aux_streams:
+        _aux_streams[key] = torch.cuda.Stream(dev)
+    return _aux_streams[key]
+
+
 def latent_forward_packed(fw: FoldedLatent, tokens: torch.Tensor, item_off: torch.Tensor, max_tokens: int = 65536):
     """Varlen latent-attention pooling: tokens [T, d] (packed, fp32/bf16), item_off int64/int32 [B+1] on the
     host or device -> pooled [B, d] fp32.  Items are processed in chunks of at most `max_tokens` tokens."""
@@ -504,7 +514,13 @@ def latent_forward_packed(fw: FoldedLatent, tokens: torch.Tensor, item_off: torc
         i1 = int(torch.searchsorted(off_host, off_host[i0] + max_tokens, right=True).item()) - 1
         i1 = max(i1, i0 + 1)
         t0, t1 = int(off_host[i0]), int(off_host[i1])
-        local_off = (off_host[i0:i1 + 1] - t0).to(torch.int32).to(dev)
+        # the few KB of offsets cross on a side stream: a pageable copy on the compute stream would make the host wait
+        # for everything queued there (the previous chunk's pooling) and stall the caller's upload pipeline
+        side = _aux_stream(dev)
+        with torch.cuda.stream(side):
+            local_off = (off_host[i0:i1 + 1] - t0).to(torch.int32).to(dev)
+        torch.cuda.current_stream().wait_stream(side)
+        local_off.record_stream(torch.cuda.current_stream())
         check(lib.nrb_latent_forward_packed(C.byref(fw.struct), ptr(tokens[t0:t1]), dtype_code(tokens.dtype), t1 - t0,
                                             ptr(local_off), i1 - i0, ptr(out[i0:i1]), ptr(ws), ws.numel(),
                                             stream_ptr()), "nrb_latent_forward_packed")
