@@ -157,12 +157,19 @@ def test_score_rank_edge_cases(ops):
     assert not torch.isnan(scores[4:]).any()
 
 
-def test_unsupported_dim_is_an_error(ops):
+def test_odd_widths_run_padded_and_oversized_rows_are_an_error(ops):
+    """A width that is no 512-byte multiple (100 fp32 elements) runs on zero-padded tables and gives the cosine of
+    the logical row; rows beyond the kernel's 4 KB are an error at the C ABI, not undefined behaviour."""
     from news_recommendation_project_v2_b200._lib import NrbError
-    T = torch.randn(8, 100).cuda()
+    g = torch.Generator().manual_seed(3)
+    T = torch.randn(8, 100, generator=g).cuda()
+    one = lambda v: torch.tensor([v], dtype=torch.int32).cuda()
+    user, scores, ranks = ops.score_rank(1, T, None, T, one(2), _csr([1]), one(5), _csr([1]), 1, want_user=True)
+    want = torch.nn.functional.cosine_similarity(T[2].double(), T[5].double(), dim=0)
+    assert user.shape == (1, 100) and abs(float(scores[0]) - float(want)) < 1e-6 and int(ranks[0]) == 1
+    big = torch.randn(4, 1280).cuda()  # 5 KB rows
     with pytest.raises(NrbError):
-        ops.score_rank(1, T, None, T, torch.zeros(1, dtype=torch.int32).cuda(), _csr([1]),
-                       torch.zeros(1, dtype=torch.int32).cuda(), _csr([1]), 1)
+        ops.score_rank(1, big, None, big, one(0), _csr([1]), one(1), _csr([1]), 1)
 
 
 def test_topk_order_bit_exact(ops):
