@@ -161,6 +161,7 @@ class ScoringEngine:
         if getattr(self, "_fa_weights_key", None) != fp:
             self._fa_weights = _final_attention_weights(self.model, self.dtype, dev)
             self._fa_weights_key = fp
+        self._padded = None
         self.cand = torch.empty(n, d, dtype=self.dtype, device=dev)
         self.hist_x = torch.empty(n, d, dtype=self.dtype, device=dev)
         self.hist_e = torch.empty(n, d, dtype=self.dtype, device=dev)
@@ -303,6 +304,8 @@ class ScoringEngine:
     def prepare_user_encoder(self, hist_src: torch.Tensor) -> None:
         from .attention import NewAttention
         from .latent_attention import LatentAttentionModel
+
+        self._padded = None  # new tables may land at the old addresses: padded kernel copies are rebuilt
 
         if isinstance(self.model, NewAttention):
             # LayerNorm chain + exp(linear1): per-row, same exp-weighted pooling as FinalAttention

@@ -118,6 +118,7 @@ class ShardedTableEngine(ScoringEngine):
             if self.gather == "nvls":
                 self._build_nvls(local_rows, fw if latent else None, None if latent else w)
                 self._stream_barrier()
+                self._padded = None
                 self.cand = self._cand_table if self._cand_table is not None else full["cand"][:n]
                 self.hist_x = full["hist_x"][:n]
                 self.hist_e = None if latent else full["hist_e"][:n]
@@ -194,6 +195,7 @@ class ShardedTableEngine(ScoringEngine):
                                                 group=self.group)
             # every rank's pushes have landed before anybody scores
             self._stream_barrier()
+            self._padded = None
             self.cand = self._cand_table if self._cand_table is not None else full["cand"][:n]
             self.hist_x = full["hist_x"][:n]
             self.hist_e = None if latent else full["hist_e"][:n]

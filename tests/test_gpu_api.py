@@ -436,6 +436,15 @@ def test_row_width_384_runs_on_zero_padded_tables(precision, tol):
     s_h, r_h = eng.score_host(t(imp.hist_idx), t(syn.csr_offsets(imp.hist_len)), t(imp.cand_idx),
                               t(syn.csr_offsets(imp.cand_len)), n_chunks=3)
     assert torch.equal(s_h, s_dev.cpu()) and torch.equal(r_h, r_dev.cpu())
+    # new weights on the SAME engine: the padded kernel copies must follow the rebuilt tables (which may well land
+    # at the old addresses)
+    with torch.no_grad():
+        model.linear3.bias.add_(0.25)
+    eng.prepare_user_encoder(eng.cand)
+    _, s_new, r_new = eng.score(imp.hist_idx, imp.hist_len, imp.cand_idx, imp.cand_len)
+    _, s_fresh, r_fresh = ScoringEngine(table, model, precision=precision).score(imp.hist_idx, imp.hist_len,
+                                                                                 imp.cand_idx, imp.cand_len)
+    assert torch.equal(s_new, s_fresh) and torch.equal(r_new, r_fresh) and not torch.equal(s_new, s_dev)
     # module forward on a padded, masked batch
     groups = group_items(imp.hist_idx[:int(imp.hist_len[:20].sum())], imp.hist_len[:20])
     emb, mask = final_attention_eval_collate_fn(list(groups), table)
